@@ -1,0 +1,725 @@
+"""Python face of the B200 array core: the same `al.*` names and semantics as the reference's
+arraylib/core.py, bound with ctypes to libarraylib_b200.so (device-resident float32 buffers).
+
+Reference citations (/root/reference/arraylib/core.py) are given per function. Differences from
+the reference that a caller can observe are listed in DESIGN.md ("Deviations"); in short:
+`to_numpy` is an owning device->host copy of the logical view, `apply`/`reduce` callables must
+resolve to a named device kernel (else NotImplementedError), scalar-on-the-left arithmetic works,
+and C-level failures raise Python exceptions instead of aborting the interpreter.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import functools as ft
+import typing as tp
+from io import StringIO
+
+from . import ufuncs as _uf
+from ._lib import (BINOPS, REDOPS, UFUNCS, ArrayP, CLayout, check_ptr, check_rc, lib, raise_last_error,
+                   size_array)
+
+Number = (int, float)
+
+
+class Layout(tp.NamedTuple):  # core.py:40-43
+    shape: tuple
+    stride: tuple
+    ndim: int
+
+
+# -------------------------------------------------------------------------------------------------
+# NDArray (core.py:46-199)
+# -------------------------------------------------------------------------------------------------
+
+
+class NDArray:
+    """Float32 N-d array whose buffer lives in GPU HBM. `buffer` is the C `NDArray*` handle."""
+
+    __slots__ = ("buffer", "__weakref__")
+
+    def __init__(self, buffer):
+        self.buffer = check_ptr(buffer)
+
+    # -- metadata, read straight from the host-side C structs ------------------------------------
+    @property
+    def ndim(self) -> int:
+        return int(self.buffer.contents.lay.contents.ndim)
+
+    @property
+    def shape(self) -> tuple:
+        lay = self.buffer.contents.lay.contents
+        return tuple(int(lay.shape[i]) for i in range(lay.ndim))
+
+    @property
+    def stride(self) -> tuple:
+        lay = self.buffer.contents.lay.contents
+        return tuple(int(lay.stride[i]) for i in range(lay.ndim))
+
+    @property
+    def size(self) -> int:  # element count of the BASE buffer, like core.py:61-62
+        return int(self.buffer.contents.data.contents.size)
+
+    @property
+    def view(self) -> bool:
+        return bool(self.buffer.contents.view)
+
+    @property
+    def layout(self) -> Layout:
+        return Layout(self.shape, self.stride, self.ndim)
+
+    @property
+    def T(self):
+        return self.transpose(list(range(self.ndim - 1, -1, -1)))
+
+    # -- methods mirroring the free functions -----------------------------------------------------
+    def reshape(self, shape):
+        return reshape(self, shape)
+
+    def transpose(self, dst):
+        return transpose(self, dst)
+
+    def move_dim(self, src, dst):
+        return move_dim(self, src, dst)
+
+    def ravel(self):
+        return ravel(self)
+
+    def as_strided(self, *, shape, stride):
+        return as_strided(self, shape, stride)
+
+    def reduce_sum(self, *, dims=None):
+        return reduce_sum(self, dims=dims)
+
+    def reduce_max(self, *, dims=None):
+        return reduce_max(self, dims=dims)
+
+    def reduce_min(self, *, dims=None):
+        return reduce_min(self, dims=dims)
+
+    def where(self, lhs, rhs):
+        return where(self, lhs, rhs)
+
+    def cat(self, arrays, *, dims):
+        return cat([self] + list(arrays), dims)
+
+    def apply(self, fn):
+        return apply(fn, self)
+
+    # -- operators ---------------------------------------------------------------------------------
+    def __add__(self, other):
+        return add(self, other)
+
+    def __radd__(self, other):
+        return add(other, self)
+
+    def __sub__(self, other):
+        return sub(self, other)
+
+    def __rsub__(self, other):
+        return sub(other, self)
+
+    def __mul__(self, other):
+        return mul(self, other)
+
+    def __rmul__(self, other):
+        return mul(other, self)
+
+    def __truediv__(self, other):
+        return div(self, other)
+
+    def __rtruediv__(self, other):
+        return div(other, self)
+
+    def __pow__(self, other):
+        return pow(self, other)
+
+    def __neg__(self):
+        return neg(self)
+
+    def __matmul__(self, other):
+        return matmul(self, other)
+
+    def __lt__(self, other):
+        return lt(self, other)
+
+    def __le__(self, other):
+        return le(self, other)
+
+    def __gt__(self, other):
+        return gt(self, other)
+
+    def __ge__(self, other):
+        return ge(self, other)
+
+    def __eq__(self, other):
+        return eq(self, other)
+
+    def __ne__(self, other):
+        return ne(self, other)
+
+    __hash__ = None
+
+    def __getitem__(self, index):
+        return getitem(self, index)
+
+    def __setitem__(self, index, value):
+        return setitem(self, index, value)
+
+    def __copy__(self):
+        return copy(self)
+
+    def __deepcopy__(self, memo):
+        return copy(self, deep=True)
+
+    def __float__(self) -> float:  # core.py:187-189: element 0 of the base buffer
+        assert self.size == 1
+        out = C.c_float()
+        check_rc(lib.array_read_base(self.buffer, 0, 1, C.byref(out)))
+        return float(out.value)
+
+    def __int__(self) -> int:
+        return int(float(self))
+
+    def __len__(self) -> int:
+        return self.size
+
+    def __array__(self, dtype=None, copy=None):
+        out = to_numpy(self)
+        return out if dtype is None else out.astype(dtype)
+
+    def __str__(self) -> str:
+        return ppstr(self)
+
+    def __repr__(self) -> str:
+        return pprepr(self)
+
+    def __del__(self):
+        free(self)
+
+
+def _new(ptr) -> NDArray:
+    return NDArray(ptr)
+
+
+def free(array) -> None:  # core.py:330-332 (idempotent here)
+    buf = getattr(array, "buffer", None)
+    if buf:
+        array.buffer = None
+        try:
+            lib.array_free(buf)
+        except Exception:  # interpreter shutdown
+            pass
+
+
+def synchronize() -> None:
+    """Block until every enqueued kernel has finished (the library is asynchronous)."""
+    check_rc(lib.al_sync())
+
+
+# -------------------------------------------------------------------------------------------------
+# helpers (core.py:207-244)
+# -------------------------------------------------------------------------------------------------
+
+
+def cdiv(a, b):
+    return (a + b - 1) // b
+
+
+def normalize_index(index):
+    return tuple(index) if isinstance(index, tp.Sequence) else (index,)
+
+
+def slice_to_range(shape, ndim, slices):
+    assert isinstance(slices, tp.Sequence)
+    assert all(isinstance(s, slice) for s in slices)
+    assert len(slices) == ndim
+    start = tuple(s.start or 0 for s in slices)
+    end = tuple(s.stop or shape[i] for i, s in enumerate(slices))
+    step = tuple(s.step or 1 for s in slices)
+    assert all(0 <= lo < hi <= shape[i] for i, (lo, hi) in enumerate(zip(start, end)))
+    return start, end, step
+
+
+@ft.cache
+def is_broadcastable(lhs: Layout, rhs: Layout) -> bool:
+    for le_, re_ in zip(reversed(lhs.shape), reversed(rhs.shape)):
+        if le_ != re_ and le_ != 1 and re_ != 1:
+            return False
+    return True
+
+
+def _int_seq(seq, what):
+    assert isinstance(seq, tp.Sequence), f"{what} must be a sequence"
+    assert all(isinstance(i, int) for i in seq), f"{what} must hold ints"
+    return tuple(seq)
+
+
+# -------------------------------------------------------------------------------------------------
+# creation (core.py:252-327)
+# -------------------------------------------------------------------------------------------------
+
+
+def array(elems) -> NDArray:
+    assert isinstance(elems, tp.Sequence)
+    extents: dict = {}
+    flat: list = []
+
+    def walk(node, depth):
+        if not isinstance(node, tp.Sequence):
+            assert isinstance(node, Number), f"elems={node!r}"
+            flat.append(float(node))
+            return
+        if depth in extents:
+            assert extents[depth] == len(node), f"dim={depth} mismatch: {extents[depth]}!={len(node)}"
+        else:
+            extents[depth] = len(node)
+        for child in node:
+            walk(child, depth + 1)
+
+    walk(elems, 0)
+    shape = tuple(extents.values())
+    host = (C.c_float * len(flat))(*flat)
+    return _new(lib.array_fill(host, size_array(shape), len(shape)))
+
+
+def ones(shape) -> NDArray:
+    shape = _int_seq(shape, "shape")
+    return _new(lib.array_ones(size_array(shape), len(shape)))
+
+
+def zeros(shape) -> NDArray:
+    shape = _int_seq(shape, "shape")
+    return _new(lib.array_zeros(size_array(shape), len(shape)))
+
+
+def full(shape, value) -> NDArray:
+    shape = _int_seq(shape, "shape")
+    return _new(lib.array_full(size_array(shape), len(shape), float(value)))
+
+
+def arange(start: int, end: tp.Optional[int] = None, step: int = 1) -> NDArray:
+    if end is None:
+        start, end = 0, start
+    assert isinstance(start, int) and isinstance(end, int) and isinstance(step, int)
+    assert (0 <= start < end) and (step > 0)
+    return _new(lib.array_arange(start, end, step))
+
+
+def linspace(start: int, end: int, n: int) -> NDArray:
+    assert isinstance(start, int) and isinstance(end, int) and isinstance(n, int)
+    assert (0 <= start < end) and (n > 0)
+    return _new(lib.array_linspace(start, end, n))
+
+
+# -------------------------------------------------------------------------------------------------
+# host <-> device (core.py:340-363)
+# -------------------------------------------------------------------------------------------------
+
+
+def from_numpy(array) -> NDArray:
+    """Upload a float32 numpy array (any strides; 0-d becomes shape (1,))."""
+    import numpy as np
+
+    assert isinstance(array, np.ndarray), f"expected numpy array, got {type(array)=}"
+    assert array.dtype == np.float32, f"expected float32 dtype, got {array.dtype=}"
+    host = np.ascontiguousarray(array)
+    shape = host.shape if host.ndim else (1,)
+    return _new(lib.array_fill(C.c_void_p(host.ctypes.data), size_array(shape), len(shape)))
+
+
+def to_numpy(array: NDArray, out=None):
+    """Device -> host COPY of the logical view (honours strides and the view offset).
+
+    `out` (optional, extension): a C-contiguous float32 array of the same shape to copy into,
+    e.g. one backed by pinned memory from `host_buffer`."""
+    import numpy as np
+
+    assert isinstance(array, NDArray)
+    if out is None:
+        out = np.empty(array.shape, dtype=np.float32)
+    else:
+        assert isinstance(out, np.ndarray) and out.dtype == np.float32 and out.flags.c_contiguous
+        assert out.shape == array.shape
+    check_rc(lib.array_to_host(array.buffer, C.c_void_p(out.ctypes.data)))
+    return out
+
+
+def host_buffer(shape):
+    """float32 numpy array backed by PINNED host memory (extension; for fast from_numpy/to_numpy
+    staging). The memory is released when the array and all its views are garbage collected."""
+    import numpy as np
+
+    n = int(np.prod(shape)) if len(tuple(shape)) else 1
+    ptr = lib.al_host_alloc(max(n, 1) * 4)
+    if not ptr:
+        raise_last_error()
+    raw = (C.c_float * max(n, 1)).from_address(ptr)
+    keeper = _PinnedOwner(ptr, raw)
+    arr = np.frombuffer(keeper, dtype=np.float32, count=n).reshape(shape)
+    return arr
+
+
+class _PinnedOwner:
+    """Buffer-protocol owner of one pinned allocation; frees it when collected."""
+
+    def __init__(self, ptr, raw):
+        self._ptr, self._raw = ptr, raw
+
+    def __buffer__(self, flags):
+        return memoryview(self._raw)
+
+    def __del__(self):
+        try:
+            lib.al_host_free(self._ptr)
+        except Exception:
+            pass
+
+
+# -------------------------------------------------------------------------------------------------
+# binary ops (core.py:371-414)
+# -------------------------------------------------------------------------------------------------
+
+_COMMUTATIVE = {"sum", "mul", "max", "min", "eq", "ne"}
+_MIRROR = {"gt": "lt", "lt": "gt", "ge": "le", "le": "ge"}
+
+
+def generate_binary_op(op: str):
+    code = BINOPS.index(op)
+
+    def wrapper(lhs, rhs):
+        if isinstance(lhs, NDArray) and isinstance(rhs, NDArray):
+            assert is_broadcastable(lhs.layout, rhs.layout), "cannot broadcast shapes"
+            return _new(lib.array_array_op_named(code, lhs.buffer, rhs.buffer))
+        if isinstance(lhs, NDArray) and isinstance(rhs, Number):
+            return _new(lib.array_scalar_op_named(code, lhs.buffer, float(rhs)))
+        if isinstance(lhs, Number) and isinstance(rhs, NDArray):
+            # The reference raises NotImplementedError here (core.py:381); supported as
+            # a superset: swap when the op allows it, else broadcast a one-element array.
+            if op in _COMMUTATIVE:
+                return wrapper(rhs, lhs)
+            if op in _MIRROR:
+                return globals()[_MIRROR[op]](rhs, lhs)
+            return wrapper(full((1,), lhs), rhs)
+        raise NotImplementedError(f"Not supported for {type(lhs)=} and {type(rhs)=}")
+
+    wrapper.__doc__ = f"Binary {op} operation"
+    wrapper.__name__ = f"array_array_{op}"
+    return wrapper
+
+
+add = generate_binary_op("sum")
+sub = generate_binary_op("sub")
+mul = generate_binary_op("mul")
+div = generate_binary_op("div")
+mod = generate_binary_op("mod")
+pow = generate_binary_op("pow")
+max = generate_binary_op("max")
+min = generate_binary_op("min")
+eq = generate_binary_op("eq")
+ne = generate_binary_op("ne")
+gt = generate_binary_op("gt")
+ge = generate_binary_op("ge")
+lt = generate_binary_op("lt")
+le = generate_binary_op("le")
+
+
+def matmul(lhs, rhs) -> NDArray:
+    assert lhs.shape[-1] == rhs.shape[0]
+    assert lhs.ndim == 2 and rhs.ndim == 2
+    return _new(lib.array_array_matmul(lhs.buffer, rhs.buffer))
+
+
+def dot(lhs, rhs) -> NDArray:
+    assert isinstance(lhs, NDArray) and isinstance(rhs, NDArray)
+    assert lhs.ndim == 1 and rhs.ndim == 1, "dot product requires 1D arrays"
+    return _new(lib.array_array_dot(lhs.buffer, rhs.buffer))
+
+
+# -------------------------------------------------------------------------------------------------
+# unary ufunc table and apply (core.py:422-460)
+# -------------------------------------------------------------------------------------------------
+
+
+def generate_unary_op(op: str):
+    code = UFUNCS.index(op)
+
+    def wrapper(array):
+        assert isinstance(array, NDArray)
+        return _new(lib.array_op_named(code, array.buffer))
+
+    wrapper.__doc__ = f"Elementwise {op} operation"
+    wrapper.__name__ = f"array_{op}"
+    return wrapper
+
+
+neg = generate_unary_op("neg")
+abs = generate_unary_op("abs")
+sqrt = generate_unary_op("sqrt")
+exp = generate_unary_op("exp")
+log = generate_unary_op("log")
+sin = generate_unary_op("sin")
+cos = generate_unary_op("cos")
+tan = generate_unary_op("tan")
+asin = generate_unary_op("asin")
+acos = generate_unary_op("acos")
+atan = generate_unary_op("atan")
+sinh = generate_unary_op("sinh")
+cosh = generate_unary_op("cosh")
+tanh = generate_unary_op("tanh")
+asinh = generate_unary_op("asinh")
+acosh = generate_unary_op("acosh")
+atanh = generate_unary_op("atanh")
+ceil = generate_unary_op("ceil")
+floor = generate_unary_op("floor")
+
+
+def apply(fn, array) -> NDArray:
+    """Elementwise map. `fn` must resolve to a named device ufunc (see ufuncs.resolve_unary)."""
+    assert callable(fn) or isinstance(fn, str)
+    assert isinstance(array, NDArray)
+    return _new(lib.array_op_named(_uf.resolve_unary(fn), array.buffer))
+
+
+# -------------------------------------------------------------------------------------------------
+# views (core.py:468-506, 788-802)
+# -------------------------------------------------------------------------------------------------
+
+
+def reshape(array, shape) -> NDArray:
+    shape = _int_seq(shape, "shape")
+    dst_total = ft.reduce(lambda x, y: x * y, shape, 1)
+    src_total = ft.reduce(lambda x, y: x * y, array.shape, 1)
+    assert src_total == dst_total, f"incorrect reshape {shape=}!={array.shape=}"
+    return _new(lib.array_reshape(array.buffer, size_array(shape), len(shape)))
+
+
+def transpose(array, dst) -> NDArray:
+    dst = _int_seq(dst, "dst")
+    assert len(dst) == array.ndim
+    return _new(lib.array_transpose(array.buffer, size_array(dst)))
+
+
+def move_dim(array, src, dst) -> NDArray:
+    assert isinstance(array, NDArray)
+    src, dst = _int_seq(src, "src"), _int_seq(dst, "dst")
+    assert len(src) == len(dst)
+    assert 0 < len(src) <= array.ndim
+    return _new(lib.array_move_dim(array.buffer, size_array(src), size_array(dst), len(src)))
+
+
+def ravel(array) -> NDArray:
+    assert isinstance(array, NDArray)
+    return _new(lib.array_ravel(array.buffer))
+
+
+def as_strided(array, shape, stride) -> NDArray:
+    assert isinstance(array, NDArray)
+    shape, stride = _int_seq(shape, "shape"), _int_seq(stride, "stride")
+    assert len(shape) == len(stride)
+    assert all(s > 0 for s in stride)
+    sh, st = size_array(shape), size_array(stride)
+    lay = CLayout(len(shape), C.cast(sh, C.POINTER(C.c_size_t)), C.cast(st, C.POINTER(C.c_size_t)))
+    return _new(lib.array_as_strided(array.buffer, C.byref(lay)))
+
+
+# -------------------------------------------------------------------------------------------------
+# indexing (core.py:514-641)
+# -------------------------------------------------------------------------------------------------
+
+
+def _range_args(array, rng):
+    start, end, step = rng
+    for part in (start, end, step):
+        assert isinstance(part, tp.Sequence)
+        assert all(isinstance(i, int) for i in part)
+    assert len(start) == len(end) == len(step) == array.ndim
+    return size_array(start), size_array(end), size_array(step)
+
+
+def get_view_from_range(array, range) -> NDArray:
+    assert isinstance(array, NDArray)
+    return _new(lib.array_get_view(array.buffer, *_range_args(array, range)))
+
+
+def get_scalar_from_index(array, index) -> float:
+    assert isinstance(array, NDArray)
+    index = _int_seq(index, "index")
+    assert len(index) == array.ndim
+    assert all(idx < array.shape[i] for i, idx in enumerate(index))
+    value = lib.array_get_elem(array.buffer, size_array(index))
+    if value != value and lib.al_last_error():
+        raise_last_error()
+    return value
+
+
+def getitem(array, index):
+    index = normalize_index(index)
+    assert len(index) == array.ndim, f"{len(index)} != {array.ndim}"
+    if all(isinstance(i, int) for i in index):
+        return get_scalar_from_index(array, index)
+    if all(isinstance(i, slice) for i in index):
+        return get_view_from_range(array, slice_to_range(array.shape, array.ndim, index))
+    raise NotImplementedError(f"Index type not supported: {index}")
+
+
+def set_elem_from_scalar(array, value, index):
+    index = _int_seq(index, "index")
+    assert len(index) == array.ndim
+    assert all(idx < array.shape[i] for i, idx in enumerate(index))
+    check_ptr(lib.array_set_elem_from_scalar(array.buffer, float(value), size_array(index)))
+    return array
+
+
+def set_view_from_scalar(array, value, index):
+    start, end, step = _range_args(array, index)
+    shape = array.shape
+    assert all(0 <= index[0][i] < index[1][i] <= shape[i] for i in range(array.ndim))
+    check_ptr(lib.array_set_view_from_scalar(array.buffer, float(value), start, end, step))
+    return array
+
+
+def set_view_from_array(array, value: NDArray, index):
+    assert array.ndim == value.ndim
+    start, end, step = index
+    assert len(start) == len(end) == len(step) == value.ndim
+    assert all(cdiv(end[i] - start[i], step[i]) == value.shape[i] for i in range(array.ndim))
+    check_ptr(lib.array_set_view_from_array(array.buffer, value.buffer, *_range_args(array, index)))
+    return array
+
+
+def setitem(array, index, value):
+    assert isinstance(array, NDArray)
+    index = normalize_index(index)
+    assert len(index) == array.ndim, "full index required to match ndim"
+    if all(isinstance(i, int) for i in index):
+        assert isinstance(value, Number), f"{type(value)=}"
+        return set_elem_from_scalar(array, value, index)
+    if all(isinstance(i, slice) for i in index):
+        rng = slice_to_range(array.shape, array.ndim, index)
+        if isinstance(value, Number):
+            return set_view_from_scalar(array, value, rng)
+        if isinstance(value, NDArray):
+            return set_view_from_array(array, value, rng)
+        raise NotImplementedError(f"Value type not supported: {value}")
+    raise NotImplementedError(f"Index type not supported: {index}")
+
+
+# -------------------------------------------------------------------------------------------------
+# copy (core.py:649-653)
+# -------------------------------------------------------------------------------------------------
+
+
+def copy(array, deep=False) -> NDArray:
+    fn = lib.array_deep_copy if deep else lib.array_shallow_copy
+    return _new(fn(array.buffer))
+
+
+# -------------------------------------------------------------------------------------------------
+# reductions (core.py:661-694)
+# -------------------------------------------------------------------------------------------------
+
+
+def _dims_arg(array, dims):
+    dims = tuple(range(array.ndim)) if dims is None else tuple(dims)
+    assert all(isinstance(i, int) for i in dims)
+    assert all(0 <= i < array.ndim for i in dims)
+    return size_array(dims), len(dims)
+
+
+def reduce(fn, array, dims=None, init=0.0) -> NDArray:
+    """Keepdims reduction with an accumulator that must resolve to sum / max / min / prod."""
+    assert isinstance(array, NDArray)
+    assert isinstance(dims, tp.Sequence) or dims is None
+    dims_c, n = _dims_arg(array, dims)
+    return _new(lib.array_reduce_named(_uf.resolve_reduce(fn), array.buffer, dims_c, n, float(init)))
+
+
+def generate_reduce_op(op: str):
+    libfn = getattr(lib, f"array_reduce_{op}")
+
+    def wrapper(array, dims=None):
+        assert isinstance(array, NDArray)
+        dims_c, n = _dims_arg(array, dims)
+        return _new(libfn(array.buffer, dims_c, n))
+
+    wrapper.__doc__ = f"Reduce an array along an axis with {op}"
+    wrapper.__name__ = f"array_reduce_{op}"
+    return wrapper
+
+
+reduce_sum = generate_reduce_op("sum")
+reduce_max = generate_reduce_op("max")
+reduce_min = generate_reduce_op("min")
+
+
+# -------------------------------------------------------------------------------------------------
+# where / cat (core.py:702-748)
+# -------------------------------------------------------------------------------------------------
+
+
+def where(cond, lhs, rhs) -> NDArray:
+    assert isinstance(cond, NDArray)
+    l_arr, r_arr = isinstance(lhs, NDArray), isinstance(rhs, NDArray)
+    if l_arr and r_arr:
+        assert cond.shape == lhs.shape == rhs.shape
+        return _new(lib.array_array_array_where(cond.buffer, lhs.buffer, rhs.buffer))
+    if l_arr and isinstance(rhs, Number):
+        assert cond.shape == lhs.shape
+        return _new(lib.array_array_scalar_where(cond.buffer, lhs.buffer, float(rhs)))
+    if isinstance(lhs, Number) and r_arr:
+        assert cond.shape == rhs.shape
+        return _new(lib.array_scalar_array_where(cond.buffer, float(lhs), rhs.buffer))
+    if isinstance(lhs, Number) and isinstance(rhs, Number):
+        return _new(lib.array_scalar_scalar_where(cond.buffer, float(lhs), float(rhs)))
+    raise NotImplementedError(f"not implemented for {type(cond)=} and {type(lhs)=}")
+
+
+def cat(arrays, dims=None) -> NDArray:
+    """Concatenate along `dims`; several dims give a block-diagonal layout padded with zeros."""
+    assert isinstance(arrays, tp.Sequence)
+    assert all(isinstance(a, NDArray) for a in arrays)
+    ndim = arrays[0].ndim
+    dims = list(dims) if dims else list(range(ndim))
+    assert all(a.ndim == ndim for a in arrays)
+    for d in range(ndim):
+        if d not in dims:
+            assert all(a.shape[d] == arrays[0].shape[d] for a in arrays)
+    out_shape = [sum(a.shape[d] for a in arrays) if d in dims else arrays[0].shape[d] for d in range(ndim)]
+    out = zeros(out_shape)
+    start = [0] * ndim
+    for a in arrays:
+        end = [start[d] + a.shape[d] if d in dims else out_shape[d] for d in range(ndim)]
+        set_view_from_array(out, a, (tuple(start), tuple(end), (1,) * ndim))
+        for d in dims:
+            start[d] += a.shape[d]
+    return out
+
+
+# -------------------------------------------------------------------------------------------------
+# printing (core.py:756-780): formats a host copy
+# -------------------------------------------------------------------------------------------------
+
+
+def pprepr(array) -> str:
+    assert isinstance(array, NDArray)
+    return f"NDArray(f32[{','.join(map(str, array.shape))}])"
+
+
+def ppstr(array) -> str:
+    assert isinstance(array, NDArray)
+    host = to_numpy(array)
+    out = StringIO()
+
+    def emit(node):
+        if node.ndim == 0:
+            out.write(f"{float(node)}")
+            return
+        out.write("[")
+        for i in range(node.shape[0]):
+            if i:
+                out.write(", ")
+            emit(node[i])
+        out.write("]")
+
+    emit(host)
+    return out.getvalue()

@@ -1,0 +1,119 @@
+// Internal declarations shared by the translation units of libarraylib_b200.so.
+// Nothing here crosses the C ABI (see include/arraylib_b200.h for that).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "arraylib_b200.h"
+
+namespace al {
+
+constexpr int kMaxDims = 8;   // folded (post-merge) rank the kernels accept
+constexpr int kNumSMs = 148;  // B200
+
+// ---- per-process runtime -------------------------------------------------------------------
+struct Runtime {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    uint64_t launches = 0;
+    const char* last_kernel = "";
+    uint64_t bytes_in_use = 0;
+    // tunables (al_set_tuning)
+    long stream_store_min_bytes = 64l << 20;  // outputs at least this big use st.global.cs
+    long ew_unroll = 4;
+    long force_general = 0;    // 1: disable the vector / tile fast paths (tests the fallback)
+    long reduce_splits = 0;    // 0 = auto
+    long disable_window = 0;
+};
+Runtime& rt();
+bool ensure_init();  // lazily al_init(-1); false (with error set) on failure
+
+// ---- error channel ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void clear_error();
+bool cuda_ok(cudaError_t e, const char* what);
+
+#define AL_CUDA(expr)                                 \
+    do {                                              \
+        if (!::al::cuda_ok((expr), #expr)) return 0;  \
+    } while (0)
+#define AL_REQUIRE(cond, ...)             \
+    do {                                  \
+        if (!(cond)) {                    \
+            ::al::set_error(__VA_ARGS__); \
+            return 0;                     \
+        }                                 \
+    } while (0)
+
+inline void note_launch(const char* name) {
+    rt().launches++;
+    rt().last_kernel = name;
+}
+bool check_launch(const char* name);  // cudaGetLastError after a launch
+
+// ---- storage ---------------------------------------------------------------------------------
+size_t count_of(const size_t* shape, size_t ndim);  // zero extents count as 1 (arraylib.c:66-72)
+NDArray* new_array(const size_t* shape, size_t ndim);  // contiguous, fresh device buffer
+NDArray* new_view(const NDArray* src, const size_t* shape, const size_t* stride, size_t ndim,
+                  size_t extra_offset);
+bool is_contiguous(const NDArray* a);
+size_t view_offset(const NDArray* a);  // ptr - mem, in elements
+bool valid(const NDArray* a, const char* who);
+
+// ---- folded layouts --------------------------------------------------------------------------
+// Dimensions are stored INNERMOST FIRST (index 0 = fastest-varying logical axis).
+struct Folded {
+    int ndim = 0;
+    uint64_t extent[kMaxDims];
+    int64_t out_stride[kMaxDims];
+    int64_t in_stride[3][kMaxDims];
+};
+// Collapse an iteration space of `ndim` logical axes over `nin` strided operands and one
+// strided output: extent-1 axes are dropped and neighbours that are mutually contiguous in every
+// operand are merged. Returns false (error set) when more than kMaxDims axes survive.
+bool fold_layout(size_t ndim, const size_t* shape, const size_t* out_stride, int nin,
+                 const size_t* const* in_stride, Folded* f);
+
+// ---- elementwise engine (elementwise.cu) -------------------------------------------------------
+enum EwKind { EW_BINARY, EW_SCALAR, EW_UNARY, EW_COPY, EW_WHERE_AAA, EW_WHERE_AAS, EW_WHERE_ASA, EW_WHERE_ASS };
+struct EwCall {
+    EwKind kind;
+    int op = 0;                    // al_binop / al_ufunc
+    float s0 = 0.f, s1 = 0.f;      // scalar operands
+    int nin = 0;
+    const float* in[3] = {nullptr, nullptr, nullptr};
+    float* out = nullptr;
+};
+// Runs `call` over a folded iteration space whose output is contiguous (out_stride ignored).
+bool launch_elementwise(const EwCall& call, const Folded& f);
+// Generic strided scatter: dst(strided) = src(strided) or scalar. Compat path (setters, cat).
+bool launch_strided_assign(float* dst, const Folded& f, const float* src, float scalar);
+
+// ---- reduce engine (reduce.cu) -----------------------------------------------------------------
+NDArray* reduce_impl(int redop, const NDArray* src, const size_t* dims, size_t ndims, float init,
+                     bool custom_init);
+
+// ---- fills (runtime.cu) ------------------------------------------------------------------------
+bool fill_const(float* p, size_t n, float v);
+
+// Every extern "C" entry point serialises on one lock (ctypes drops the GIL around calls) and
+// starts with a clean error slot.
+std::recursive_mutex& api_mutex();
+const std::string& last_error_string();
+void restore_error(const std::string& s);
+
+}  // namespace al
+
+#define AL_ENTER                                                     \
+    std::lock_guard<std::recursive_mutex> _guard(::al::api_mutex()); \
+    ::al::clear_error()

@@ -1,0 +1,612 @@
+// Reduce engine: keepdims reduction of a strided source over an arbitrary set of axes.
+//
+// Replaces array_reduce (arraylib/src/arraylib.c:690-756), which walks the SOURCE once in logical
+// order and scatters into local_acc[dst_offset] with two offset_indexer calls per element. Here
+// the axes are split on the host into a kept list and a reduced list (each folded, innermost
+// first) and one of these sm_100a kernels is chosen per call:
+//
+//   reduce_outer   the innermost kept axis is unit-stride in the source ("output-contiguous"):
+//                  threads run along the kept axis (coalesced, 128-bit when aligned), blockDim.y
+//                  and gridDim.y split the reduced range, partials meet in shared memory.
+//                  Config C4a: [64,(512*512),64] -> [64,1,1,64].
+//   reduce_inner   the innermost reduced axis is unit-stride ("reduce-contiguous"): a team of
+//                  2..32 lanes (warp shuffles) or a whole CTA per output. Config C4b: 2^24 x 64.
+//   reduce_window  overlapping as_strided windows (kept stride == reduced stride == 1): each CTA
+//                  stages a tile + halo in shared memory once and forms all window sums from
+//                  per-block prefix/suffix scans. Config C5a.
+//   reduce_finish  second pass when the reduced range was split across CTAs (long reduced
+//                  extent, few outputs): combines the per-split partials in a fixed order.
+//
+// Summation order differs from the reference (tree instead of sequential), so reduce_sum carries
+// the tolerance stated in DESIGN.md; max/min are order independent.
+#include "al_internal.h"
+#include "device_utils.cuh"
+
+namespace al {
+
+
+// accumulate step, same scalar semantics as the elementwise table (arraylib.c:12-19)
+template <int OP>
+__device__ __forceinline__ float racc(float a, float b) {
+    if constexpr (OP == AL_RSUM) return __fadd_rn(a, b);
+    else if constexpr (OP == AL_RMAX) return (a >= b || b != b) ? a : b;
+    else if constexpr (OP == AL_RMIN) return (a <= b || b != b) ? a : b;
+    else return __fmul_rn(a, b);
+}
+template <int OP>
+__device__ __forceinline__ float rident() {
+    if constexpr (OP == AL_RSUM) return 0.0f;
+    else if constexpr (OP == AL_RMAX) return -INFINITY;
+    else if constexpr (OP == AL_RMIN) return INFINITY;
+    else return 1.0f;
+}
+// The reference seeds both dst and the thread-local accumulator with `init` and then merges them
+// (arraylib.c:723-750): result = fn(init, fn(init, x0, x1, ...)).
+template <int OP>
+__device__ __forceinline__ float rfinal(float init, float v) {
+    return racc<OP>(init, racc<OP>(init, v));
+}
+
+struct RedArgs {
+    const float* src;
+    float* dst;          // final output, or the partial buffer [split][nout]
+    uint32_t nk_items;   // kept items (vector items in reduce_outer)
+    uint32_t nr_items;   // reduced items (vector items in reduce_inner)
+    uint32_t nout;       // output elements
+    int nk, nr;
+    uint32_t kext[kMaxDims];
+    FastDiv kdiv[kMaxDims];
+    long long kstride[kMaxDims];
+    uint32_t rext[kMaxDims];
+    FastDiv rdiv[kMaxDims];
+    long long rstride[kMaxDims];
+    uint32_t r_per_split;
+    float init;
+    int finalize;
+};
+
+__device__ __forceinline__ long long kept_offset(const RedArgs& a, uint32_t g) {
+    long long off = 0;
+    for (int d = 0; d < a.nk; d++) {
+        uint32_t idx;
+        if (d == a.nk - 1) {
+            idx = g;
+        } else {
+            uint32_t q = fdiv(g, a.kdiv[d]);
+            idx = g - q * a.kext[d];
+            g = q;
+        }
+        off += (long long)idx * a.kstride[d];
+    }
+    return off;
+}
+__device__ __forceinline__ long long red_offset(const RedArgs& a, uint32_t r) {
+    if (a.nr == 1) return (long long)r * a.rstride[0];
+    long long off = 0;
+    for (int d = 0; d < a.nr; d++) {
+        uint32_t idx;
+        if (d == a.nr - 1) {
+            idx = r;
+        } else {
+            uint32_t q = fdiv(r, a.rdiv[d]);
+            idx = r - q * a.rext[d];
+            r = q;
+        }
+        off += (long long)idx * a.rstride[d];
+    }
+    return off;
+}
+
+template <int VEC>
+struct Acc;
+template <>
+struct Acc<1> {
+    float v;
+};
+template <>
+struct Acc<4> {
+    float4 v;
+};
+
+template <int VEC>
+__device__ __forceinline__ Acc<VEC> ld_acc(const float* p) {
+    Acc<VEC> r;
+    if constexpr (VEC == 1) r.v = __ldcs(p);
+    else r.v = __ldcs(reinterpret_cast<const float4*>(p));
+    return r;
+}
+template <int OP, int VEC>
+__device__ __forceinline__ void acc_into(Acc<VEC>& a, const Acc<VEC>& b) {
+    if constexpr (VEC == 1) {
+        a.v = racc<OP>(a.v, b.v);
+    } else {
+        a.v.x = racc<OP>(a.v.x, b.v.x);
+        a.v.y = racc<OP>(a.v.y, b.v.y);
+        a.v.z = racc<OP>(a.v.z, b.v.z);
+        a.v.w = racc<OP>(a.v.w, b.v.w);
+    }
+}
+template <int OP, int VEC>
+__device__ __forceinline__ Acc<VEC> acc_ident() {
+    Acc<VEC> r;
+    const float i = rident<OP>();
+    if constexpr (VEC == 1) r.v = i;
+    else r.v = make_float4(i, i, i, i);
+    return r;
+}
+
+// ---- reduce_outer: threads along the kept axis --------------------------------------------------
+// grid.x tiles the kept items, grid.y the reduced range; block = (TX, TY), TX*TY = 256.
+template <int OP, int VEC>
+__global__ void __launch_bounds__(256) reduce_outer_kernel(const RedArgs a) {
+    extern __shared__ float4 smem_raw[];
+    Acc<VEC>* sm = reinterpret_cast<Acc<VEC>*>(smem_raw);
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = g < a.nk_items;
+    const uint32_t r0 = blockIdx.y * a.r_per_split;
+    const uint32_t r1 = min(r0 + a.r_per_split, a.nr_items);
+    Acc<VEC> acc = acc_ident<OP, VEC>();
+    if (live) {
+        const float* base = a.src + kept_offset(a, g) * (a.nk ? 1 : 0);
+        const uint32_t step = blockDim.y;
+        uint32_t r = r0 + threadIdx.y;
+        // 4 independent loads in flight per thread
+        for (; r + 3 * step < r1; r += 4 * step) {
+            Acc<VEC> x0 = ld_acc<VEC>(base + red_offset(a, r));
+            Acc<VEC> x1 = ld_acc<VEC>(base + red_offset(a, r + step));
+            Acc<VEC> x2 = ld_acc<VEC>(base + red_offset(a, r + 2 * step));
+            Acc<VEC> x3 = ld_acc<VEC>(base + red_offset(a, r + 3 * step));
+            acc_into<OP, VEC>(x0, x1);
+            acc_into<OP, VEC>(x2, x3);
+            acc_into<OP, VEC>(x0, x2);
+            acc_into<OP, VEC>(acc, x0);
+        }
+        for (; r < r1; r += step) {
+            Acc<VEC> x = ld_acc<VEC>(base + red_offset(a, r));
+            acc_into<OP, VEC>(acc, x);
+        }
+    }
+    if (blockDim.y > 1) {
+        sm[threadIdx.y * blockDim.x + threadIdx.x] = acc;
+        __syncthreads();
+        if (threadIdx.y != 0) return;
+        for (uint32_t y = 1; y < blockDim.y; y++) acc_into<OP, VEC>(acc, sm[y * blockDim.x + threadIdx.x]);
+    }
+    if (!live) return;
+    float* dst = a.dst + (size_t)blockIdx.y * a.nout + (size_t)g * VEC;
+    if constexpr (VEC == 1) {
+        dst[0] = a.finalize ? rfinal<OP>(a.init, acc.v) : acc.v;
+    } else {
+        float4 o = acc.v;
+        if (a.finalize) {
+            o.x = rfinal<OP>(a.init, o.x);
+            o.y = rfinal<OP>(a.init, o.y);
+            o.z = rfinal<OP>(a.init, o.z);
+            o.w = rfinal<OP>(a.init, o.w);
+        }
+        *reinterpret_cast<float4*>(dst) = o;
+    }
+}
+
+// ---- reduce_inner: a team of lanes along the reduced axis ----------------------------------------
+template <int OP, int VEC>
+__device__ __forceinline__ float acc_collapse(const Acc<VEC>& a) {
+    if constexpr (VEC == 1) return a.v;
+    else return racc<OP>(racc<OP>(a.v.x, a.v.y), racc<OP>(a.v.z, a.v.w));
+}
+
+// TEAM in {1,2,4,8,16,32}: sub-warp teams, one output per team (grid.y splits the reduced range).
+template <int OP, int VEC, int TEAM>
+__global__ void __launch_bounds__(256) reduce_inner_kernel(const RedArgs a) {
+    const uint32_t gt = (blockIdx.x * 256u + threadIdx.x) / TEAM;  // team id == output id
+    const uint32_t lane = threadIdx.x % TEAM;
+    const bool live = gt < a.nout;
+    const uint32_t r0 = blockIdx.y * a.r_per_split;
+    const uint32_t r1 = min(r0 + a.r_per_split, a.nr_items);
+    Acc<VEC> acc = acc_ident<OP, VEC>();
+    if (live) {
+        const float* base = a.src + (a.nk ? kept_offset(a, gt) : 0);
+        uint32_t r = r0 + lane;
+        for (; r + 3 * TEAM < r1; r += 4 * TEAM) {
+            Acc<VEC> x0 = ld_acc<VEC>(base + red_offset(a, r));
+            Acc<VEC> x1 = ld_acc<VEC>(base + red_offset(a, r + TEAM));
+            Acc<VEC> x2 = ld_acc<VEC>(base + red_offset(a, r + 2 * TEAM));
+            Acc<VEC> x3 = ld_acc<VEC>(base + red_offset(a, r + 3 * TEAM));
+            acc_into<OP, VEC>(x0, x1);
+            acc_into<OP, VEC>(x2, x3);
+            acc_into<OP, VEC>(x0, x2);
+            acc_into<OP, VEC>(acc, x0);
+        }
+        for (; r < r1; r += TEAM) {
+            Acc<VEC> x = ld_acc<VEC>(base + red_offset(a, r));
+            acc_into<OP, VEC>(acc, x);
+        }
+    }
+    float v = acc_collapse<OP, VEC>(acc);
+#pragma unroll
+    for (int o = TEAM / 2; o > 0; o >>= 1) v = racc<OP>(v, __shfl_down_sync(0xffffffffu, v, o, TEAM));
+    if (live && lane == 0) {
+        float* dst = a.dst + (size_t)blockIdx.y * a.nout + gt;
+        *dst = a.finalize ? rfinal<OP>(a.init, v) : v;
+    }
+}
+
+// One CTA per (output, split): long reduced extents.
+template <int OP, int VEC>
+__global__ void __launch_bounds__(256) reduce_inner_cta_kernel(const RedArgs a) {
+    __shared__ float warp_part[8];
+    const uint32_t o = blockIdx.x;
+    const uint32_t r0 = blockIdx.y * a.r_per_split;
+    const uint32_t r1 = min(r0 + a.r_per_split, a.nr_items);
+    const float* base = a.src + (a.nk ? kept_offset(a, o) : 0);
+    Acc<VEC> acc = acc_ident<OP, VEC>();
+    uint32_t r = r0 + threadIdx.x;
+    for (; r + 3 * 256 < r1; r += 4 * 256) {
+        Acc<VEC> x0 = ld_acc<VEC>(base + red_offset(a, r));
+        Acc<VEC> x1 = ld_acc<VEC>(base + red_offset(a, r + 256));
+        Acc<VEC> x2 = ld_acc<VEC>(base + red_offset(a, r + 512));
+        Acc<VEC> x3 = ld_acc<VEC>(base + red_offset(a, r + 768));
+        acc_into<OP, VEC>(x0, x1);
+        acc_into<OP, VEC>(x2, x3);
+        acc_into<OP, VEC>(x0, x2);
+        acc_into<OP, VEC>(acc, x0);
+    }
+    for (; r < r1; r += 256) {
+        Acc<VEC> x = ld_acc<VEC>(base + red_offset(a, r));
+        acc_into<OP, VEC>(acc, x);
+    }
+    float v = acc_collapse<OP, VEC>(acc);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v = racc<OP>(v, __shfl_down_sync(0xffffffffu, v, s));
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) v = racc<OP>(v, warp_part[w]);
+        float* dst = a.dst + (size_t)blockIdx.y * a.nout + o;
+        *dst = a.finalize ? rfinal<OP>(a.init, v) : v;
+    }
+}
+
+// ---- reduce_finish: out[o] = final(sum_s partial[s][o]) ------------------------------------------
+template <int OP>
+__global__ void __launch_bounds__(256)
+reduce_finish_kernel(const float* __restrict__ partial, float* __restrict__ out, uint32_t nout, uint32_t splits,
+                     float init) {
+    if (nout <= 2048) {  // one warp per output, lanes stride over the splits
+        const uint32_t o = (blockIdx.x * 256u + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+        float v = rident<OP>();
+        if (o < nout)
+            for (uint32_t s = lane; s < splits; s += 32) v = racc<OP>(v, partial[(size_t)s * nout + o]);
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) v = racc<OP>(v, __shfl_down_sync(0xffffffffu, v, k));
+        if (o < nout && lane == 0) out[o] = rfinal<OP>(init, v);
+    } else {
+        const uint32_t o = blockIdx.x * 256u + threadIdx.x;
+        if (o >= nout) return;
+        float v = rident<OP>();
+        for (uint32_t s = 0; s < splits; s++) v = racc<OP>(v, partial[(size_t)s * nout + o]);
+        out[o] = rfinal<OP>(init, v);
+    }
+}
+
+// ---- reduce_window: overlapping windows, out[i] = sum_{j<w} x[i+j] --------------------------------
+// Each CTA owns WT consecutive outputs and stages x[i0 .. i0+WT+w-2] in shared memory. The staged
+// span is cut into blocks of w; with P = inclusive prefix scan and S = inclusive suffix scan inside
+// each block, a window that starts at block offset k is S[k] (rest of its block) + P[k-1] of the
+// next block, i.e. 2 shared reads + 1 add per output instead of w reads (van Herk / Gil-Werman).
+// The per-block scans are done by one thread per block with stride-(w+1) padding so the 32 lanes of
+// a warp hit 32 different banks.
+constexpr int kWinThreads = 256;
+template <int OP>
+__global__ void __launch_bounds__(kWinThreads)
+reduce_window_kernel(const float* __restrict__ x, float* __restrict__ out, uint32_t nout, uint32_t w, uint32_t nblk,
+                     float init) {
+    extern __shared__ float wsm[];
+    const uint32_t pitch = w + 1;               // padded block pitch
+    float* P = wsm;                             // [nblk+1][pitch] prefix scans
+    float* S = wsm + (size_t)(nblk + 1) * pitch;  // [nblk+1][pitch] suffix scans
+    const uint32_t tile = nblk * w;             // outputs per CTA
+    const size_t i0 = (size_t)blockIdx.x * tile;
+    const size_t n_in = (size_t)nout + w - 1;   // valid source elements
+    const uint32_t span = tile + w;             // staged elements (one extra block covers the halo)
+    for (uint32_t e = threadIdx.x; e < span; e += kWinThreads) {
+        const size_t gi = i0 + e;
+        const float v = gi < n_in ? __ldcs(x + gi) : rident<OP>();
+        const uint32_t b = e / w, k = e - b * w;
+        P[b * pitch + k] = v;
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b <= nblk; b += kWinThreads) {
+        float* p = P + b * pitch;
+        float* s = S + b * pitch;
+        float run = p[w - 1];
+        s[w - 1] = run;
+        for (int k = (int)w - 2; k >= 0; k--) {
+            run = racc<OP>(p[k], run);
+            s[k] = run;
+        }
+        run = p[0];
+        for (uint32_t k = 1; k < w; k++) {
+            run = racc<OP>(run, p[k]);
+            p[k] = run;
+        }
+    }
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < tile; e += kWinThreads) {
+        const size_t gi = i0 + e;
+        if (gi >= nout) break;
+        const uint32_t b = e / w, k = e - b * w;
+        float v = S[b * pitch + k];
+        if (k) v = racc<OP>(v, P[(b + 1) * pitch + k - 1]);
+        __stcs(out + gi, rfinal<OP>(init, v));
+    }
+}
+
+// ---- host planning ------------------------------------------------------------------------------------
+struct AxisList {
+    int n = 0;
+    uint64_t extent[kMaxDims];
+    int64_t stride[kMaxDims];
+    bool push(uint64_t e, int64_t s) {  // called innermost first; merges when contiguous
+        if (n > 0 && s == stride[n - 1] * (int64_t)extent[n - 1]) {
+            extent[n - 1] *= e;
+            return true;
+        }
+        if (n == kMaxDims) return false;
+        extent[n] = e;
+        stride[n] = s;
+        n++;
+        return true;
+    }
+    uint64_t count() const {
+        uint64_t c = 1;
+        for (int i = 0; i < n; i++) c *= extent[i];
+        return c;
+    }
+};
+
+static uint32_t pow2_ceil(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+template <int OP>
+static bool run_reduce(const float* src, float* out, const AxisList& K, const AxisList& R, float init) {
+    Runtime& r = rt();
+    cudaStream_t st = r.stream;
+    const uint64_t nout = K.count(), rtot = R.count();
+    if (nout >= (1ull << 31) || rtot >= (1ull << 31)) {
+        set_error("NotImplementedError: reduce with >= 2^31 outputs or reduced elements per output");
+        return false;
+    }
+    RedArgs a;
+    memset(&a, 0, sizeof a);
+    a.src = src;
+    a.nout = (uint32_t)nout;
+    a.init = init;
+    a.nk = K.n;
+    a.nr = R.n;
+    const bool general = r.force_general;
+
+    // -- overlapping windows (C5a) --
+    if (!general && !r.disable_window && K.n == 1 && R.n == 1 && K.stride[0] == 1 && R.stride[0] == 1 &&
+        R.extent[0] >= 8 && R.extent[0] <= 1024 && nout >= 4 * R.extent[0]) {
+        const uint32_t w = (uint32_t)R.extent[0];
+        uint32_t nblk = 8192 / w;  // ~8K outputs per CTA
+        if (nblk < 1) nblk = 1;
+        size_t smem = 2ull * (nblk + 1) * (w + 1) * sizeof(float);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(reduce_window_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const uint32_t tile = nblk * w;
+        unsigned blocks = (unsigned)((nout + tile - 1) / tile);
+        reduce_window_kernel<OP><<<blocks, kWinThreads, smem, st>>>(src, out, (uint32_t)nout, w, nblk, init);
+        note_launch("reduce_window");
+        return check_launch("reduce_window");
+    }
+
+    const bool outer = K.n > 0 && K.stride[0] == 1 && !(R.n > 0 && R.stride[0] == 1 && K.extent[0] < 8);
+    const bool aligned = (uintptr_t)src % 16 == 0;
+    for (int d = 0; d < K.n; d++) {
+        a.kext[d] = (uint32_t)K.extent[d];
+        a.kstride[d] = K.stride[d];
+    }
+    for (int d = 0; d < R.n; d++) {
+        a.rext[d] = (uint32_t)R.extent[d];
+        a.rstride[d] = R.stride[d];
+    }
+    if (R.n == 0) {  // nothing to reduce: one pass that only applies the init fold
+        a.nr = 1;
+        a.rext[0] = 1;
+        a.rstride[0] = 0;
+    }
+    auto all_mult4 = [](const AxisList& L, int from) {
+        for (int d = from; d < L.n; d++)
+            if (L.stride[d] % 4 != 0) return false;
+        return true;
+    };
+    const int target_ctas = kNumSMs * 8;
+    float* partial = nullptr;
+
+    if (outer) {
+        const bool vec = !general && aligned && K.extent[0] % 4 == 0 && all_mult4(K, 1) && all_mult4(R, 0);
+        const int VEC = vec ? 4 : 1;
+        a.kext[0] = (uint32_t)(K.extent[0] / VEC);
+        a.kstride[0] = VEC;
+        a.nk_items = (uint32_t)(nout / VEC);
+        a.nr_items = (uint32_t)rtot;
+        for (int d = 0; d < kMaxDims; d++) {
+            a.kdiv[d] = make_fastdiv(a.kext[d] ? a.kext[d] : 1);
+            a.rdiv[d] = make_fastdiv(a.rext[d] ? a.rext[d] : 1);
+        }
+        const unsigned TY = rtot >= 64 ? 8 : 1, TX = 256 / TY;
+        const unsigned gx = (a.nk_items + TX - 1) / TX;
+        unsigned splits = 1;
+        if (r.reduce_splits > 0) splits = (unsigned)r.reduce_splits;
+        else if (gx < (unsigned)target_ctas) splits = (target_ctas + gx - 1) / gx;
+        unsigned max_splits = (unsigned)((rtot + TY * 8 - 1) / (TY * 8));
+        if (splits > max_splits) splits = max_splits ? max_splits : 1;
+        if (splits > 65535) splits = 65535;
+        a.r_per_split = (uint32_t)((rtot + splits - 1) / splits);
+        splits = (unsigned)((rtot + a.r_per_split - 1) / a.r_per_split);
+        a.finalize = splits == 1;
+        if (splits > 1) {
+            if (!cuda_ok(cudaMallocAsync((void**)&partial, (size_t)splits * nout * sizeof(float), st), "cudaMallocAsync(partials)")) return false;
+            a.dst = partial;
+        } else {
+            a.dst = out;
+        }
+        size_t smem = TY > 1 ? (size_t)256 * sizeof(float) * VEC : 0;
+        dim3 grid(gx, splits), block(TX, TY);
+        if (vec) reduce_outer_kernel<OP, 4><<<grid, block, smem, st>>>(a);
+        else reduce_outer_kernel<OP, 1><<<grid, block, smem, st>>>(a);
+        note_launch(vec ? "reduce_outer_vec4" : "reduce_outer_scalar");
+        if (!check_launch("reduce_outer")) return false;
+        if (splits > 1) {
+            unsigned fb = nout <= 2048 ? (unsigned)((nout * 32 + 255) / 256) : (unsigned)((nout + 255) / 256);
+            reduce_finish_kernel<OP><<<fb, 256, 0, st>>>(partial, out, (uint32_t)nout, splits, init);
+            note_launch("reduce_finish");
+            cudaFreeAsync(partial, st);
+            return check_launch("reduce_finish");
+        }
+        return true;
+    }
+
+    // inner (team) path; also the generic fallback when nothing is unit-stride
+    const bool vec = !general && aligned && R.n > 0 && R.stride[0] == 1 && R.extent[0] % 4 == 0 && all_mult4(R, 1) &&
+                     all_mult4(K, 0);
+    const int VEC = vec ? 4 : 1;
+    if (vec) {
+        a.rext[0] = (uint32_t)(R.extent[0] / 4);
+        a.rstride[0] = 4;
+    }
+    a.nk_items = (uint32_t)nout;
+    a.nr_items = (uint32_t)(rtot / VEC);
+    for (int d = 0; d < kMaxDims; d++) {
+        a.kdiv[d] = make_fastdiv(a.kext[d] ? a.kext[d] : 1);
+        a.rdiv[d] = make_fastdiv(a.rext[d] ? a.rext[d] : 1);
+    }
+    const bool cta_team = a.nr_items >= 4096 && nout * 32 < (uint64_t)target_ctas * 256;
+    unsigned splits = 1;
+    if (cta_team) {
+        if (r.reduce_splits > 0) splits = (unsigned)r.reduce_splits;
+        else if (nout < (uint64_t)target_ctas) splits = (unsigned)((target_ctas + nout - 1) / nout);
+        unsigned max_splits = (a.nr_items + 2047) / 2048;
+        if (splits > max_splits) splits = max_splits;
+        if (splits > 65535) splits = 65535;
+        if (splits < 1) splits = 1;
+    }
+    a.r_per_split = (a.nr_items + splits - 1) / splits;
+    splits = (a.nr_items + a.r_per_split - 1) / a.r_per_split;
+    a.finalize = splits == 1;
+    if (splits > 1) {
+        if (!cuda_ok(cudaMallocAsync((void**)&partial, (size_t)splits * nout * sizeof(float), st), "cudaMallocAsync(partials)")) return false;
+        a.dst = partial;
+    } else {
+        a.dst = out;
+    }
+    if (cta_team) {
+        dim3 grid((unsigned)nout, splits);
+        if (vec) reduce_inner_cta_kernel<OP, 4><<<grid, 256, 0, st>>>(a);
+        else reduce_inner_cta_kernel<OP, 1><<<grid, 256, 0, st>>>(a);
+        note_launch("reduce_inner_cta");
+    } else {
+        uint32_t team = pow2_ceil((a.nr_items + 3) / 4);
+        if (team > 32) team = 32;
+        unsigned gx = (unsigned)(((uint64_t)nout * team + 255) / 256);
+#define AL_TEAM_CASE(T)                                                               \
+    case T:                                                                           \
+        if (vec) reduce_inner_kernel<OP, 4, T><<<dim3(gx, 1), 256, 0, st>>>(a);       \
+        else reduce_inner_kernel<OP, 1, T><<<dim3(gx, 1), 256, 0, st>>>(a);           \
+        break;
+        switch (team) {
+            AL_TEAM_CASE(1)
+            AL_TEAM_CASE(2)
+            AL_TEAM_CASE(4)
+            AL_TEAM_CASE(8)
+            AL_TEAM_CASE(16)
+            AL_TEAM_CASE(32)
+        }
+#undef AL_TEAM_CASE
+        note_launch(vec ? "reduce_inner_vec4" : "reduce_inner_scalar");
+    }
+    if (!check_launch("reduce_inner")) return false;
+    if (splits > 1) {
+        unsigned fb = nout <= 2048 ? (unsigned)((nout * 32 + 255) / 256) : (unsigned)((nout + 255) / 256);
+        reduce_finish_kernel<OP><<<fb, 256, 0, st>>>(partial, out, (uint32_t)nout, splits, init);
+        note_launch("reduce_finish");
+        cudaFreeAsync(partial, st);
+        return check_launch("reduce_finish");
+    }
+    return true;
+}
+
+NDArray* reduce_impl(int redop, const NDArray* src, const size_t* dims, size_t ndims, float init, bool custom_init) {
+    if (!valid(src, "array_reduce")) return nullptr;
+    AL_REQUIRE(redop >= 0 && redop < AL_REDOP_COUNT, "ValueError: unknown reduce op %d", redop);
+    const size_t nd = src->lay->ndim;
+    AL_REQUIRE(nd <= 64, "ValueError: too many dimensions");
+    bool red[64] = {false};
+    for (size_t i = 0; i < ndims; i++) {
+        AL_REQUIRE(dims[i] < nd, "ValueError: out of bounds");
+        red[dims[i]] = true;
+    }
+    size_t dshape[64];
+    for (size_t i = 0; i < nd; i++) dshape[i] = red[i] ? 1 : src->lay->shape[i];
+    AxisList K, R;
+    for (size_t ax = nd; ax-- > 0;) {  // innermost first
+        uint64_t e = src->lay->shape[ax];
+        if (e == 1) continue;
+        bool ok = (red[ax] ? R : K).push(e, (int64_t)src->lay->stride[ax]);
+        AL_REQUIRE(ok, "NotImplementedError: reduce layout needs more than %d non-mergeable axes", kMaxDims);
+    }
+    NDArray* out = new_array(dshape, nd);
+    if (!out) return nullptr;
+    if (!custom_init) {
+        const float ident[AL_REDOP_COUNT] = {0.0f, -INFINITY, INFINITY, 1.0f};
+        init = ident[redop];
+    }
+    bool ok = false;
+    switch (redop) {
+        case AL_RSUM: ok = run_reduce<AL_RSUM>(src->ptr, out->ptr, K, R, init); break;
+        case AL_RMAX: ok = run_reduce<AL_RMAX>(src->ptr, out->ptr, K, R, init); break;
+        case AL_RMIN: ok = run_reduce<AL_RMIN>(src->ptr, out->ptr, K, R, init); break;
+        case AL_RPROD: ok = run_reduce<AL_RPROD>(src->ptr, out->ptr, K, R, init); break;
+    }
+    if (!ok) {
+        std::string keep = last_error_string();
+        array_free(out);
+        restore_error(keep);
+        return nullptr;
+    }
+    return out;
+}
+
+}  // namespace al
+
+using namespace al;
+
+extern "C" {
+
+NDArray* array_reduce_named(int redop, const NDArray* src, const size_t* dims, size_t ndims, f32 init) {
+    AL_ENTER;
+    return reduce_impl(redop, src, dims, ndims, init, true);
+}
+NDArray* array_reduce_sum(const NDArray* src, const size_t* dims, size_t ndims) {  // arraylib.c:758-760
+    AL_ENTER;
+    return reduce_impl(AL_RSUM, src, dims, ndims, 0.f, false);
+}
+NDArray* array_reduce_max(const NDArray* src, const size_t* dims, size_t ndims) {  // arraylib.c:762-764
+    AL_ENTER;
+    return reduce_impl(AL_RMAX, src, dims, ndims, 0.f, false);
+}
+NDArray* array_reduce_min(const NDArray* src, const size_t* dims, size_t ndims) {  // arraylib.c:766-768
+    AL_ENTER;
+    return reduce_impl(AL_RMIN, src, dims, ndims, 0.f, false);
+}
+NDArray* array_reduce(binop, const NDArray*, const size_t*, size_t, f32) {
+    AL_ENTER;
+    set_error("NotImplementedError: host callbacks cannot run on the device; use array_reduce_named with an al_redop entry");
+    return nullptr;
+}
+
+}  // extern "C"

@@ -1,0 +1,660 @@
+// Runtime, storage, initialisers, host materialisation and metadata-only views.
+// Reference behaviour restated from arraylib/src/arraylib.c (line ranges cited per function);
+// the design (device pool, stream ordering, error channel) is new.
+#include "al_internal.h"
+
+namespace al {
+
+static Runtime g_rt;
+static thread_local std::string g_err;
+static std::recursive_mutex g_api_mutex;
+
+Runtime& rt() { return g_rt; }
+std::recursive_mutex& api_mutex() { return g_api_mutex; }
+const std::string& last_error_string() { return g_err; }
+void restore_error(const std::string& s) { g_err = s; }
+
+void set_error(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+void clear_error() { g_err.clear(); }
+
+bool cuda_ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    const char* cls = (e == cudaErrorMemoryAllocation) ? "MemoryError" : "RuntimeError";
+    set_error("%s: CUDA failure %s in %s", cls, cudaGetErrorString(e), what);
+    return false;
+}
+
+bool check_launch(const char* name) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return true;
+    set_error("RuntimeError: launch of %s failed: %s", name, cudaGetErrorString(e));
+    return false;
+}
+
+bool ensure_init() { return g_rt.device >= 0 || al_init(-1) == 0; }
+
+size_t count_of(const size_t* shape, size_t ndim) {
+    size_t n = 1;
+    for (size_t i = 0; i < ndim; i++) n *= shape[i] ? shape[i] : 1;
+    return n;
+}
+
+bool valid(const NDArray* a, const char* who) {
+    if (a && a->data && a->lay && a->lay->ndim > 0 && a->ptr) return true;
+    set_error("TypeError: %s got a NULL or malformed array", who);
+    return false;
+}
+
+size_t view_offset(const NDArray* a) { return (size_t)(a->ptr - a->data->mem); }
+
+// arraylib.c:91-98
+bool is_contiguous(const NDArray* a) {
+    size_t expect = 1;
+    for (size_t i = a->lay->ndim; i-- > 0;) {
+        if (a->lay->stride[i] != expect) return false;
+        expect *= a->lay->shape[i];
+    }
+    return true;
+}
+
+static Layout* make_layout(const size_t* shape, const size_t* stride, size_t ndim) {
+    Layout* lay = (Layout*)malloc(sizeof(Layout));
+    lay->ndim = ndim;
+    lay->shape = (size_t*)malloc(sizeof(size_t) * ndim);
+    lay->stride = (size_t*)malloc(sizeof(size_t) * ndim);
+    memcpy(lay->shape, shape, sizeof(size_t) * ndim);
+    if (stride) {
+        memcpy(lay->stride, stride, sizeof(size_t) * ndim);
+    } else {  // row-major (arraylib.c:102-107)
+        size_t run = 1;
+        for (size_t i = ndim; i-- > 0;) {
+            lay->stride[i] = run;
+            run *= shape[i];
+        }
+    }
+    return lay;
+}
+
+static void free_layout(Layout* lay) {
+    if (!lay) return;
+    free(lay->shape);
+    free(lay->stride);
+    free(lay);
+}
+
+// arraylib.c:129-137 + 212-221, with the buffer taken from the stream-ordered device pool.
+NDArray* new_array(const size_t* shape, size_t ndim) {
+    if (!ensure_init()) return nullptr;
+    AL_REQUIRE(ndim > 0 && shape, "ValueError: non-positive ndim");
+    for (size_t i = 0; i < ndim; i++)
+        AL_REQUIRE(shape[i] > 0, "ValueError: zero extent in shape (axis %zu)", i);
+    size_t n = count_of(shape, ndim);
+    float* mem = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&mem, n * sizeof(float), g_rt.stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("MemoryError: failed to allocate %zu bytes of device memory (%s)", n * sizeof(float),
+                  cudaGetErrorString(e));
+        return nullptr;
+    }
+    Data* d = (Data*)malloc(sizeof(Data));
+    d->mem = mem;
+    d->size = n;
+    d->refs = 1;
+    g_rt.bytes_in_use += n * sizeof(float);
+    NDArray* a = (NDArray*)malloc(sizeof(NDArray));
+    a->data = d;
+    a->ptr = mem;
+    a->lay = make_layout(shape, nullptr, ndim);
+    a->view = false;
+    return a;
+}
+
+// arraylib.c:237-246 / 258-269: a second NDArray over the same Data.
+NDArray* new_view(const NDArray* src, const size_t* shape, const size_t* stride, size_t ndim,
+                  size_t extra_offset) {
+    NDArray* a = (NDArray*)malloc(sizeof(NDArray));
+    a->data = src->data;
+    __atomic_add_fetch(&src->data->refs, 1, __ATOMIC_RELAXED);
+    a->ptr = src->ptr + extra_offset;
+    a->lay = make_layout(shape, stride, ndim);
+    a->view = true;
+    return a;
+}
+
+// ---- fills -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fill_const_kernel(float* __restrict__ p, size_t n, float v) {
+    size_t n4 = n >> 2;
+    float4 vv = make_float4(v, v, v, v);
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
+        reinterpret_cast<float4*>(p)[i] = vv;
+    for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+// value(i) = float(start + (first + i) * step) with the product formed in exact integers
+__global__ void __launch_bounds__(256)
+fill_iota_kernel(float* __restrict__ p, size_t n, unsigned long long start, unsigned long long step) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        p[i] = (float)(start + i * step);
+}
+
+// linspace body (arraylib.c:313-314): p[i] = start + p[i] * dx, fused like the reference build
+__global__ void __launch_bounds__(256) axpb_kernel(float* __restrict__ p, size_t n, float dx, float start) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        p[i] = fmaf(p[i], dx, start);
+}
+
+static int fill_grid(size_t work) {
+    size_t blocks = (work + 255) / 256;
+    size_t cap = (size_t)kNumSMs * 16;
+    return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+bool fill_const(float* p, size_t n, float v) {
+    fill_const_kernel<<<fill_grid(n / 4 + 4), 256, 0, g_rt.stream>>>(p, n, v);
+    note_launch("fill_const");
+    return check_launch("fill_const");
+}
+
+}  // namespace al
+
+using namespace al;
+
+extern "C" {
+
+// ---- runtime -------------------------------------------------------------------------------------
+int al_init(int device) {
+    AL_ENTER;
+    if (g_rt.device >= 0) return 0;
+    if (device < 0) {
+        const char* e = getenv("ARRAYLIB_DEVICE");
+        if (!e) e = getenv("LOCAL_RANK");
+        device = e ? atoi(e) : 0;
+    }
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        set_error("RuntimeError: no CUDA device available (%s); arraylib_b200 has no CPU fallback",
+                  err == cudaSuccess ? "device count is 0" : cudaGetErrorString(err));
+        return -1;
+    }
+    if (device >= count) device = device % count;
+    if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return -1;
+    if (!cuda_ok(cudaStreamCreateWithFlags(&g_rt.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return -1;
+    if (!cuda_ok(cudaEventCreate(&g_rt.ev_start), "cudaEventCreate")) return -1;
+    if (!cuda_ok(cudaEventCreate(&g_rt.ev_stop), "cudaEventCreate")) return -1;
+    cudaMemPool_t pool;
+    if (cuda_ok(cudaDeviceGetDefaultMemPool(&pool, device), "cudaDeviceGetDefaultMemPool")) {
+        uint64_t keep = UINT64_MAX;  // cache freed blocks instead of returning them to the driver
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    g_rt.device = device;
+    clear_error();
+    return 0;
+}
+
+int al_device(void) { return g_rt.device; }
+
+int al_sync(void) {
+    AL_ENTER;
+    if (g_rt.device < 0) return 0;
+    return cuda_ok(cudaStreamSynchronize(g_rt.stream), "cudaStreamSynchronize") ? 0 : -1;
+}
+
+void* al_stream(void) { return (void*)g_rt.stream; }
+const char* al_last_error(void) { return g_err.c_str(); }
+const char* al_version(void) { return "arraylib_b200 0.1 (sm_100a)"; }
+uint64_t al_launch_count(void) { return g_rt.launches; }
+const char* al_last_kernel(void) { return g_rt.last_kernel; }
+uint64_t al_bytes_in_use(void) { return g_rt.bytes_in_use; }
+
+int al_timer_start(void) {
+    AL_ENTER;
+    if (!ensure_init()) return -1;
+    return cuda_ok(cudaEventRecord(g_rt.ev_start, g_rt.stream), "cudaEventRecord") ? 0 : -1;
+}
+
+int al_timer_stop(float* ms) {
+    AL_ENTER;
+    if (!ensure_init()) return -1;
+    if (!cuda_ok(cudaEventRecord(g_rt.ev_stop, g_rt.stream), "cudaEventRecord")) return -1;
+    if (!cuda_ok(cudaEventSynchronize(g_rt.ev_stop), "cudaEventSynchronize")) return -1;
+    return cuda_ok(cudaEventElapsedTime(ms, g_rt.ev_start, g_rt.ev_stop), "cudaEventElapsedTime") ? 0 : -1;
+}
+
+// A small pool of events so that a caller (bench.py) can bracket individual operations on the
+// library stream without synchronising between them: record now, read elapsed times after al_sync.
+static std::vector<cudaEvent_t> g_events;
+
+int al_event_record(int idx) {
+    AL_ENTER;
+    if (!ensure_init()) return -1;
+    if (idx < 0 || idx >= 1 << 16) return set_error("IndexError: event index %d out of range", idx), -1;
+    while ((int)g_events.size() <= idx) {
+        cudaEvent_t e;
+        if (!cuda_ok(cudaEventCreate(&e), "cudaEventCreate")) return -1;
+        g_events.push_back(e);
+    }
+    return cuda_ok(cudaEventRecord(g_events[idx], g_rt.stream), "cudaEventRecord") ? 0 : -1;
+}
+
+int al_event_elapsed(int first, int second, float* ms) {
+    AL_ENTER;
+    if (first < 0 || second < 0 || first >= (int)g_events.size() || second >= (int)g_events.size())
+        return set_error("IndexError: event was never recorded"), -1;
+    if (!cuda_ok(cudaEventSynchronize(g_events[second]), "cudaEventSynchronize")) return -1;
+    return cuda_ok(cudaEventElapsedTime(ms, g_events[first], g_events[second]), "cudaEventElapsedTime") ? 0 : -1;
+}
+
+int al_trim_pool(void) {
+    AL_ENTER;
+    if (!ensure_init()) return -1;
+    cudaMemPool_t pool;
+    if (!cuda_ok(cudaStreamSynchronize(g_rt.stream), "sync")) return -1;
+    if (!cuda_ok(cudaDeviceGetDefaultMemPool(&pool, g_rt.device), "pool")) return -1;
+    return cuda_ok(cudaMemPoolTrimTo(pool, 0), "cudaMemPoolTrimTo") ? 0 : -1;
+}
+
+void* al_host_alloc(size_t bytes) {
+    AL_ENTER;
+    if (!ensure_init()) return nullptr;
+    void* p = nullptr;
+    if (!cuda_ok(cudaHostAlloc(&p, bytes, cudaHostAllocDefault), "cudaHostAlloc")) return nullptr;
+    return p;
+}
+
+int al_host_free(void* p) {
+    AL_ENTER;
+    return cuda_ok(cudaFreeHost(p), "cudaFreeHost") ? 0 : -1;
+}
+
+int al_set_tuning(const char* key, long value) {
+    AL_ENTER;
+    std::string k = key ? key : "";
+    if (k == "stream_store_min_bytes") g_rt.stream_store_min_bytes = value;
+    else if (k == "ew_unroll") g_rt.ew_unroll = value;
+    else if (k == "force_general") g_rt.force_general = value;
+    else if (k == "reduce_splits") g_rt.reduce_splits = value;
+    else if (k == "disable_window") g_rt.disable_window = value;
+    else {
+        set_error("KeyError: unknown tuning key '%s'", k.c_str());
+        return -1;
+    }
+    return 0;
+}
+
+// ---- storage -------------------------------------------------------------------------------------
+NDArray* array_empty(const size_t* shape, size_t ndim) {
+    AL_ENTER;
+    return new_array(shape, ndim);
+}
+
+// arraylib.c:223-231. The device block is returned to the pool in stream order, so kernels
+// already enqueued against it finish first.
+void array_free(NDArray* a) {
+    AL_ENTER;
+    if (!a) {
+        set_error("TypeError: array_free on NULL");
+        return;
+    }
+    if (a->data && __atomic_sub_fetch(&a->data->refs, 1, __ATOMIC_ACQ_REL) == 0) {
+        g_rt.bytes_in_use -= a->data->size * sizeof(float);
+        if (a->data->mem) cudaFreeAsync(a->data->mem, g_rt.stream);
+        free(a->data);
+    }
+    free_layout(a->lay);
+    free(a);
+}
+
+NDArray* array_shallow_copy(const NDArray* src) {
+    AL_ENTER;
+    if (!valid(src, "array_shallow_copy")) return nullptr;
+    return new_view(src, src->lay->shape, src->lay->stride, src->lay->ndim, 0);
+}
+
+// ---- initialisers --------------------------------------------------------------------------------
+NDArray* array_full(const size_t* shape, size_t ndim, f32 value) {
+    AL_ENTER;
+    NDArray* a = new_array(shape, ndim);
+    if (!a) return nullptr;
+    if (!fill_const(a->ptr, a->data->size, value)) {
+        array_free(a);
+        return nullptr;
+    }
+    return a;
+}
+
+NDArray* array_zeros(const size_t* shape, size_t ndim) { return array_full(shape, ndim, 0.0f); }
+NDArray* array_ones(const size_t* shape, size_t ndim) { return array_full(shape, ndim, 1.0f); }
+
+// arraylib.c:282-288 -- `elems` is a host buffer; this is the H2D upload path.
+NDArray* array_fill(f32* elems, const size_t* shape, size_t ndim) {
+    AL_ENTER;
+    AL_REQUIRE(elems, "TypeError: array_fill got a NULL host buffer");
+    NDArray* a = new_array(shape, ndim);
+    if (!a) return nullptr;
+    bool ok = cuda_ok(cudaMemcpyAsync(a->ptr, elems, a->data->size * sizeof(float), cudaMemcpyHostToDevice,
+                                      g_rt.stream), "cudaMemcpyAsync(H2D)") &&
+              cuda_ok(cudaStreamSynchronize(g_rt.stream), "cudaStreamSynchronize");
+    if (!ok) {
+        std::string keep = g_err;
+        array_free(a);
+        g_err = keep;
+        return nullptr;
+    }
+    return a;
+}
+
+// arraylib.c:298-308. While every value and every partial sum stays <= 2^24 the reference's
+// size_t -> f32 -> size_t round trip is exact and the sequence is start + i*step: that prefix is
+// produced on the device in closed form. Past 2^24 the f32 add rounds (and, for step 1, sticks at
+// 16777216 forever), so the tail replays the reference's recurrence step by step on the host and
+// is uploaded; a fixed point is detected and filled on the device instead.
+NDArray* array_arange(f32 start, f32 end, f32 step) {
+    AL_ENTER;
+    AL_REQUIRE(start < end && start >= 0, "ValueError: invalid array range.");
+    size_t span = (size_t)(end - start), st = (size_t)step;
+    AL_REQUIRE(st > 0, "ValueError: arange step must be >= 1");
+    size_t total = (span + st - 1) / st;
+    AL_REQUIRE(total > 0, "ValueError: empty arange");
+    size_t shape1[1] = {total};
+    NDArray* a = new_array(shape1, 1);
+    if (!a) return nullptr;
+    const size_t lim = (size_t)1 << 24;
+    size_t s0 = (size_t)start;
+    size_t n_exact = 0;
+    if ((float)st == step && s0 <= lim) {
+        n_exact = (lim - s0) / st + 1;
+        if (n_exact > total) n_exact = total;
+    }
+    bool ok = true;
+    if (n_exact) {
+        fill_iota_kernel<<<fill_grid(n_exact), 256, 0, g_rt.stream>>>(a->ptr, n_exact, s0, st);
+        note_launch("fill_iota");
+        ok = check_launch("fill_iota");
+    }
+    if (ok && n_exact < total) {
+        size_t running = n_exact ? s0 + (n_exact - 1) * st : s0;
+        size_t i = n_exact ? n_exact - 1 : 0;  // element i holds `running`
+        std::vector<float> host;
+        const size_t chunk = (size_t)1 << 22;
+        size_t first = i;  // index of host[0]
+        for (; i < total && ok; i++) {
+            host.push_back((float)running);
+            size_t next = (size_t)((float)running + step);
+            bool stuck = (next == running);
+            running = next;
+            if (host.size() == chunk || i + 1 == total || stuck) {
+                ok = cuda_ok(cudaMemcpyAsync(a->ptr + first, host.data(), host.size() * sizeof(float),
+                                             cudaMemcpyHostToDevice, g_rt.stream), "cudaMemcpyAsync(H2D)") &&
+                     cuda_ok(cudaStreamSynchronize(g_rt.stream), "cudaStreamSynchronize");
+                first = i + 1;
+                host.clear();
+                if (ok && stuck && i + 1 < total) {
+                    ok = fill_const(a->ptr + i + 1, total - (i + 1), (float)running);
+                    break;
+                }
+            }
+        }
+    }
+    if (!ok) {
+        std::string keep = g_err;
+        array_free(a);
+        g_err = keep;
+        return nullptr;
+    }
+    return a;
+}
+
+// arraylib.c:310-316
+NDArray* array_linspace(f32 start, f32 end, f32 n) {
+    AL_ENTER;
+    f32 dx = (end - start) / (n - 1);
+    NDArray* a = array_arange(0, n, 1);
+    if (!a) return nullptr;
+    axpb_kernel<<<fill_grid(a->data->size), 256, 0, g_rt.stream>>>(a->ptr, a->data->size, dx, start);
+    note_launch("linspace_axpb");
+    if (!check_launch("linspace_axpb")) {
+        array_free(a);
+        return nullptr;
+    }
+    return a;
+}
+
+// ---- host materialisation ------------------------------------------------------------------------
+int array_to_host(const NDArray* src, f32* dst) {
+    AL_ENTER;
+    if (!valid(src, "array_to_host")) return -1;
+    if (!dst) {
+        set_error("TypeError: array_to_host got a NULL destination");
+        return -1;
+    }
+    size_t n = count_of(src->lay->shape, src->lay->ndim);
+    const NDArray* from = src;
+    NDArray* tmp = nullptr;
+    if (!is_contiguous(src)) {
+        tmp = array_deep_copy(src);
+        if (!tmp) return -1;
+        from = tmp;
+    }
+    bool ok = cuda_ok(cudaMemcpyAsync(dst, from->ptr, n * sizeof(float), cudaMemcpyDeviceToHost, g_rt.stream),
+                      "cudaMemcpyAsync(D2H)") &&
+              cuda_ok(cudaStreamSynchronize(g_rt.stream), "cudaStreamSynchronize");
+    if (tmp) {
+        std::string keep = g_err;
+        array_free(tmp);
+        g_err = keep;
+    }
+    return ok ? 0 : -1;
+}
+
+int array_read_base(const NDArray* src, size_t offset, size_t count, f32* dst) {
+    AL_ENTER;
+    if (!valid(src, "array_read_base")) return -1;
+    if (offset + count > src->data->size) {
+        set_error("IndexError: base read [%zu, %zu) exceeds %zu elements", offset, offset + count, src->data->size);
+        return -1;
+    }
+    bool ok = cuda_ok(cudaMemcpyAsync(dst, src->data->mem + offset, count * sizeof(float), cudaMemcpyDeviceToHost,
+                                      g_rt.stream), "cudaMemcpyAsync(D2H)") &&
+              cuda_ok(cudaStreamSynchronize(g_rt.stream), "cudaStreamSynchronize");
+    return ok ? 0 : -1;
+}
+
+int array_write_base(NDArray* dst, size_t offset, size_t count, const f32* src) {
+    AL_ENTER;
+    if (!valid(dst, "array_write_base")) return -1;
+    if (offset + count > dst->data->size) {
+        set_error("IndexError: base write [%zu, %zu) exceeds %zu elements", offset, offset + count, dst->data->size);
+        return -1;
+    }
+    bool ok = cuda_ok(cudaMemcpyAsync(dst->data->mem + offset, src, count * sizeof(float), cudaMemcpyHostToDevice,
+                                      g_rt.stream), "cudaMemcpyAsync(H2D)") &&
+              cuda_ok(cudaStreamSynchronize(g_rt.stream), "cudaStreamSynchronize");
+    return ok ? 0 : -1;
+}
+
+// ---- element access ------------------------------------------------------------------------------
+static bool flat_index(const NDArray* a, const size_t* index, size_t* out) {
+    size_t off = 0;
+    for (size_t i = 0; i < a->lay->ndim; i++) {
+        if (index[i] >= a->lay->shape[i]) {
+            set_error("IndexError: index %zu out of bounds for axis %zu with extent %zu", index[i], i, a->lay->shape[i]);
+            return false;
+        }
+        off += index[i] * a->lay->stride[i];
+    }
+    if (view_offset(a) + off >= a->data->size) {
+        set_error("IndexError: element offset outside the base buffer");
+        return false;
+    }
+    *out = off;
+    return true;
+}
+
+f32 array_get_elem(const NDArray* a, const size_t* index) {
+    AL_ENTER;
+    size_t off;
+    f32 v = __builtin_nanf("");
+    if (!valid(a, "array_get_elem") || !flat_index(a, index, &off)) return v;
+    if (cuda_ok(cudaMemcpyAsync(&v, a->ptr + off, sizeof(float), cudaMemcpyDeviceToHost, g_rt.stream), "D2H"))
+        cuda_ok(cudaStreamSynchronize(g_rt.stream), "cudaStreamSynchronize");
+    return v;
+}
+
+NDArray* array_set_elem_from_scalar(NDArray* a, f32 value, const size_t* index) {
+    AL_ENTER;
+    size_t off;
+    if (!valid(a, "array_set_elem_from_scalar") || !flat_index(a, index, &off)) return nullptr;
+    if (!fill_const(a->ptr + off, 1, value)) return nullptr;
+    return a;
+}
+
+// ---- views ---------------------------------------------------------------------------------------
+static bool check_range(const NDArray* a, const size_t* start, const size_t* end, const size_t* step) {
+    for (size_t i = 0; i < a->lay->ndim; i++) {
+        if (!(start[i] < end[i])) return set_error("ValueError: start index >= end index."), false;
+        if (!(end[i] <= a->lay->shape[i])) return set_error("ValueError: end index out of bounds."), false;
+        if (!(step[i] > 0)) return set_error("ValueError: non-positive step size."), false;
+    }
+    return true;
+}
+
+// arraylib.c:326-349
+NDArray* array_get_view(const NDArray* src, const size_t* start, const size_t* end, const size_t* step) {
+    AL_ENTER;
+    if (!valid(src, "array_get_view") || !check_range(src, start, end, step)) return nullptr;
+    size_t nd = src->lay->ndim, shape[64], stride[64], off = 0;
+    AL_REQUIRE(nd <= 64, "ValueError: too many dimensions");
+    for (size_t i = 0; i < nd; i++) {
+        shape[i] = (end[i] - start[i] + step[i] - 1) / step[i];
+        stride[i] = src->lay->stride[i] * step[i];
+        off += start[i] * src->lay->stride[i];
+    }
+    AL_REQUIRE(view_offset(src) + off < src->data->size, "ValueError: offset >= size.");
+    return new_view(src, shape, stride, nd, off);
+}
+
+// arraylib.c:258-269, plus a bounds check the reference lacks: an out-of-range device access
+// would poison the CUDA context instead of merely reading garbage.
+NDArray* array_as_strided(const NDArray* src, const Layout* lay) {
+    AL_ENTER;
+    if (!valid(src, "array_as_strided")) return nullptr;
+    AL_REQUIRE(lay && lay->ndim > 0, "ValueError: ndim must be positive.");
+    size_t reach = 0;
+    for (size_t i = 0; i < lay->ndim; i++) {
+        AL_REQUIRE(lay->shape[i] > 0, "ValueError: zero extent in as_strided shape");
+        reach += (lay->shape[i] - 1) * lay->stride[i];
+    }
+    AL_REQUIRE(view_offset(src) + reach < src->data->size,
+               "ValueError: as_strided view reaches element %zu of a %zu-element buffer",
+               view_offset(src) + reach, src->data->size);
+    return new_view(src, lay->shape, lay->stride, lay->ndim, 0);
+}
+
+// Returns a contiguous alias of src: a view when src already is contiguous, else a gathered copy
+// (arraylib.c:423,433,455,479).
+static NDArray* contiguous_alias(const NDArray* src) {
+    return is_contiguous(src) ? new_view(src, src->lay->shape, src->lay->stride, src->lay->ndim, 0)
+                              : array_deep_copy(src);
+}
+
+static void relabel(NDArray* a, const size_t* shape, const size_t* stride, size_t ndim) {
+    free_layout(a->lay);
+    a->lay = make_layout(shape, stride, ndim);
+}
+
+// arraylib.c:421-430. Like the reference, the element count is checked against the BASE buffer.
+NDArray* array_reshape(const NDArray* src, const size_t* shape, size_t ndim) {
+    AL_ENTER;
+    if (!valid(src, "array_reshape")) return nullptr;
+    AL_REQUIRE(ndim > 0, "ValueError: non-positive ndim");
+    AL_REQUIRE(count_of(shape, ndim) == src->data->size,
+               "ValueError: cannot reshape a buffer of %zu elements into %zu", src->data->size, count_of(shape, ndim));
+    AL_REQUIRE(count_of(shape, ndim) == count_of(src->lay->shape, src->lay->ndim),
+               "ValueError: reshape of a view whose element count differs from its base buffer");
+    NDArray* dst = contiguous_alias(src);
+    if (!dst) return nullptr;
+    relabel(dst, shape, nullptr, ndim);
+    return dst;
+}
+
+// arraylib.c:432-442. For a contiguous source this is the reference's metadata permutation. For a
+// non-contiguous source the reference gathers into a contiguous buffer and then permutes the OLD
+// strides over it (wrong values); here the gathered copy's own strides are permuted,
+// which yields the mathematically correct transpose.
+NDArray* array_transpose(const NDArray* src, const size_t* dims) {
+    AL_ENTER;
+    if (!valid(src, "array_transpose")) return nullptr;
+    size_t nd = src->lay->ndim, shape[64], stride[64];
+    AL_REQUIRE(nd <= 64, "ValueError: too many dimensions");
+    bool seen[64] = {false};
+    for (size_t i = 0; i < nd; i++) {
+        AL_REQUIRE(dims[i] < nd && !seen[dims[i]], "ValueError: transpose axes are not a permutation");
+        seen[dims[i]] = true;
+    }
+    NDArray* dst = contiguous_alias(src);
+    if (!dst) return nullptr;
+    for (size_t i = 0; i < nd; i++) {
+        shape[i] = dst->lay->shape[dims[i]];
+        stride[i] = dst->lay->stride[dims[i]];
+    }
+    relabel(dst, shape, stride, nd);
+    return dst;
+}
+
+// arraylib.c:444-475
+NDArray* array_move_dim(const NDArray* src, const size_t* from, const size_t* to, size_t ndim) {
+    AL_ENTER;
+    if (!valid(src, "array_move_dim")) return nullptr;
+    size_t nd = src->lay->ndim;
+    AL_REQUIRE(nd <= 64, "ValueError: too many dimensions");
+    size_t to_from[64], shape[64], stride[64];
+    bool used[64] = {false};
+    for (size_t i = 0; i < nd; i++) to_from[i] = SIZE_MAX;
+    for (size_t i = 0; i < ndim; i++) {
+        AL_REQUIRE(from[i] < nd && to[i] < nd, "ValueError: out of bounds");
+        AL_REQUIRE(!used[from[i]] && to_from[to[i]] == SIZE_MAX, "ValueError: repeated axis in move_dim");
+        used[from[i]] = true;
+        to_from[to[i]] = from[i];
+    }
+    size_t j = 0;
+    for (size_t i = 0; i < nd; i++) {
+        if (to_from[i] != SIZE_MAX) continue;
+        while (j < nd && used[j]) j++;
+        to_from[i] = j++;
+    }
+    NDArray* dst = contiguous_alias(src);
+    if (!dst) return nullptr;
+    for (size_t i = 0; i < nd; i++) {
+        shape[i] = dst->lay->shape[to_from[i]];
+        stride[i] = dst->lay->stride[to_from[i]];
+    }
+    relabel(dst, shape, stride, nd);
+    return dst;
+}
+
+// arraylib.c:477-485
+NDArray* array_ravel(const NDArray* src) {
+    AL_ENTER;
+    if (!valid(src, "array_ravel")) return nullptr;
+    size_t total = count_of(src->lay->shape, src->lay->ndim);
+    NDArray* dst = contiguous_alias(src);
+    if (!dst) return nullptr;
+    size_t shape1[1] = {total}, stride1[1] = {1};
+    relabel(dst, shape1, stride1, 1);
+    return dst;
+}
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+"""Multi-GPU support: one process per GPU, arrays sharded along their LEADING axis.
+
+Nothing in the reference corresponds to this module (it is single-process).
+Design:
+  * every rank owns rows [rank*L/W, (rank+1)*L/W) of a global array whose leading extent is L;
+  * elementwise / broadcast ops are purely local; operands that are broadcast along the leading
+    axis (extent 1 or missing) are replicated on every rank;
+  * reduce over axes that exclude the leading axis is purely local (output stays sharded);
+  * reduce over a set that INCLUDES the leading axis reduces the local slab to a full-shape
+    partial and then runs ONE collective: ncclAllReduce over the partial (sum / max / min / prod);
+  * overlapping as_strided windows need a (window-1)-element halo, replicated when sharding.
+The planning functions at the top are pure host logic (tested on CPU with gloo in
+tests/test_dist_cpu.py); the collectives call NCCL through the C ABI (al_comm_*).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+# ---- pure host-side planning (no GPU, no library calls) --------------------------------------------
+
+
+def shard_bounds(extent: int, rank: int, world: int) -> tuple:
+    """[lo, hi) of the leading axis owned by `rank`: contiguous blocks, remainder to the low ranks."""
+    assert 0 <= rank < world and extent >= 0
+    base, rem = divmod(extent, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def operand_placement(global_shape, out_shape) -> str:
+    """'sharded' when the operand spans the output's leading axis, else 'replicated'
+    (its leading extent is 1 or the axis is missing: stride 0 under broadcasting)."""
+    if len(global_shape) < len(out_shape) or global_shape[0] == 1 and out_shape[0] != 1:
+        return "replicated"
+    return "sharded"
+
+
+def reduce_plan(ndim: int, dims) -> dict:
+    """What a reduce over `dims` of a leading-axis-sharded array needs."""
+    dims = tuple(range(ndim)) if dims is None else tuple(dims)
+    crosses = 0 in dims
+    return {"local_dims": dims, "collective": "allreduce" if crosses else None,
+            "output": "replicated" if crosses else "sharded"}
+
+
+def window_halo_bounds(n_out: int, window: int, rank: int, world: int) -> tuple:
+    """Base-buffer element range [lo, hi) a rank needs for its share of n_out sliding windows of
+    length `window` and stride 1: its own outputs plus a (window-1)-element halo."""
+    lo, hi = shard_bounds(n_out, rank, world)
+    return lo, hi + window - 1
+
+
+# ---- NCCL through the C ABI ---------------------------------------------------------------------------
+
+_state = {"rank": 0, "world": 1}
+
+
+def init(rank: int, world: int, unique_id: bytes | None = None, *, broadcast=None) -> None:
+    """Create the NCCL communicator. Either pass the 128-byte id obtained on rank 0 with
+    `unique_id()`, or a `broadcast(obj, src)` callable (e.g. built on torch.distributed) that
+    ships it from rank 0."""
+    from ._lib import check_rc, lib
+
+    if world == 1:
+        _state.update(rank=0, world=1)
+        return
+    if unique_id is None:
+        assert broadcast is not None
+        unique_id = broadcast(globals()["unique_id"]() if rank == 0 else None, 0)
+    assert len(unique_id) == 128
+    check_rc(lib.al_comm_init(unique_id, rank, world))
+    _state.update(rank=rank, world=world)
+
+
+def unique_id() -> bytes:
+    from ._lib import check_rc, lib
+
+    buf = C.create_string_buffer(128)
+    check_rc(lib.al_comm_unique_id(buf))
+    return buf.raw
+
+
+def rank() -> int:
+    return _state["rank"]
+
+
+def world() -> int:
+    return _state["world"]
+
+
+def allreduce(array, op: str = "sum"):
+    """In-place NCCL allreduce of a contiguous array (no-op for world == 1)."""
+    from ._lib import REDOPS, check_rc, lib
+
+    if _state["world"] > 1:
+        check_rc(lib.al_comm_allreduce(array.buffer, REDOPS.index(op)))
+    return array
+
+
+def reduce_sharded(array, op: str = "sum", dims=None):
+    """reduce_<op> of a leading-axis shard: local kernel, then one allreduce iff axis 0 is reduced."""
+    from . import core
+
+    plan = reduce_plan(array.ndim, dims)
+    part = getattr(core, f"reduce_{op}")(array, dims=plan["local_dims"])
+    if plan["collective"]:
+        allreduce(part, op)
+    return part
+
+
+def destroy() -> None:
+    from ._lib import lib
+
+    lib.al_comm_destroy()
+    _state.update(rank=0, world=1)

@@ -1,0 +1,204 @@
+"""GPU parity: broadcast binary / scalar / unary / copy / where against the CPU oracle.
+
+All elementwise, broadcast, view and copy results must be BIT-EXACT. The
+checker is oracle/oracle.c (itself pinned against the compiled reference in test_oracle.py) and,
+when oracle/_ref is present, the reference's own machine code.
+"""
+import numpy as np
+import pytest
+
+from tests.conftest import assert_bit_equal
+
+pytestmark = pytest.mark.gpu
+
+BINARY = ["sum", "sub", "mul", "div", "mod", "pow", "max", "min", "eq", "ne", "gt", "ge", "lt", "le"]
+AL_NAME = {"sum": "add"}
+EXACT_UNARY = ["neg", "abs", "sqrt", "ceil", "floor"]
+LIBM_UNARY = ["exp", "log", "sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh",
+              "atanh"]
+
+SHAPE_PAIRS = [
+    ((7,), (7,)), ((1,), (5,)), ((4, 1), (1, 6)), ((1, 2, 3), (1, 1, 2, 3)), ((1, 2, 3), (2, 1)),
+    ((5, 1, 7), (3, 1)), ((8, 1, 64), (1, 8, 64)), ((8, 8, 64), (64,)), ((3, 4, 5, 6), (5, 1)),
+    ((33, 1, 1, 36), (1, 7, 1, 36)), ((2, 3, 4, 5, 6), (4, 1, 6)), ((1024,), (1024,)), ((1031,), (1031,)),
+    ((257, 129), (129,)), ((16, 4096), (16, 1)),
+]
+
+
+def special_values(rng, shape):
+    """Random normals salted with the awkward floats: +-0, +-inf, nan, denormals, huge, tiny."""
+    x = rng.standard_normal(shape).astype(np.float32)
+    flat = x.reshape(-1)
+    specials = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-42, -1e-42, 3.4e38, -3.4e38, 1.0, -1.0, 2.0, 0.5],
+                        dtype=np.float32)
+    n = min(flat.size // 3, specials.size)
+    if n:
+        pos = rng.choice(flat.size, size=n, replace=False)
+        flat[pos] = specials[:n]
+    return x
+
+
+def fn(al, op):
+    return getattr(al, AL_NAME.get(op, op))
+
+
+@pytest.mark.parametrize("op", BINARY)
+@pytest.mark.parametrize("sa,sb", SHAPE_PAIRS)
+def test_binary_broadcast_bit_exact(al, orc, rng, op, sa, sb):
+    a, b = special_values(rng, sa), special_values(rng, sb)
+    got = al.to_numpy(fn(al, op)(al.from_numpy(a), al.from_numpy(b)))
+    assert_bit_equal(got, orc.binary(op, a, b), f"{op} {sa}x{sb}")
+
+
+@pytest.mark.parametrize("op", BINARY)
+def test_binary_against_compiled_reference(al, ref, rng, op):
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    a, b = special_values(rng, (6, 1, 40)), special_values(rng, (5, 40))
+    want = ref.binary(op, ref.from_numpy(a), ref.from_numpy(b)).numpy()
+    got = al.to_numpy(fn(al, op)(al.from_numpy(a), al.from_numpy(b)))
+    assert_bit_equal(got, want, op)
+    want = ref.binary(op, ref.from_numpy(a), 0.75).numpy()
+    assert_bit_equal(al.to_numpy(fn(al, op)(al.from_numpy(a), 0.75)), want, op + " scalar")
+
+
+@pytest.mark.parametrize("op", BINARY)
+@pytest.mark.parametrize("scalar", [1.0, -2.5, 0.0, 3.0])
+def test_scalar_ops_bit_exact(al, orc, rng, op, scalar):
+    a = special_values(rng, (5, 37))
+    got = al.to_numpy(fn(al, op)(al.from_numpy(a), scalar))
+    assert_bit_equal(got, orc.binary(op, a, scalar), f"{op} scalar {scalar}")
+
+
+def test_signed_zero_and_nan_tie_rules(al, orc):
+    """max/min: NaN-ignoring and the LEFT operand wins a +-0 tie."""
+    a = np.array([0.0, -0.0, np.nan, 1.0, np.nan, -0.0, 0.0], dtype=np.float32)
+    b = np.array([-0.0, 0.0, 1.0, np.nan, np.nan, -0.0, 0.0], dtype=np.float32)
+    for op in ("max", "min"):
+        got = al.to_numpy(fn(al, op)(al.from_numpy(a), al.from_numpy(b)))
+        assert_bit_equal(got, orc.binary(op, a, b), op)
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 1023, 4096, (1 << 20) + 3, 1 << 22])
+def test_contiguous_stream_sizes(al, orc, rng, n):
+    a = rng.standard_normal(n).astype(np.float32)
+    b = rng.standard_normal(n).astype(np.float32)
+    A, B = al.from_numpy(a), al.from_numpy(b)
+    assert_bit_equal(al.to_numpy(A + B), a + b, "add")
+    assert_bit_equal(al.to_numpy(A * B), a * b, "mul")
+    assert_bit_equal(al.to_numpy(A + 1.5), a + np.float32(1.5), "add scalar")
+
+
+def test_strided_operands(al, orc, rng):
+    base = rng.standard_normal((12, 20)).astype(np.float32)
+    other = rng.standard_normal((20, 12)).astype(np.float32)
+    A, O = al.from_numpy(base), al.from_numpy(other)
+    # transposed view (a real view: source is contiguous) + contiguous
+    assert_bit_equal(al.to_numpy(A.transpose((1, 0)) + O), base.T + other, "T + c")
+    assert_bit_equal(al.to_numpy(O + A.transpose((1, 0))), other + base.T, "c + T")
+    assert_bit_equal(al.to_numpy(A.transpose((1, 0)) * O.transpose((1, 0)).transpose((1, 0))), base.T * other, "T*T")
+    # slices with steps
+    v = A[1:11:3, 2:20:5]
+    assert v.view and v.shape == (4, 4)
+    assert_bit_equal(al.to_numpy(v), base[1:11:3, 2:20:5], "slice")
+    assert_bit_equal(al.to_numpy(v - 2.0), base[1:11:3, 2:20:5] - np.float32(2), "slice - s")
+    # overlapping as_strided windows
+    flat = al.from_numpy(base.reshape(-1))
+    w = flat.as_strided(shape=(50, 7), stride=(3, 1))
+    wn = np.lib.stride_tricks.as_strided(base.reshape(-1), shape=(50, 7), strides=(12, 4))
+    assert_bit_equal(al.to_numpy(w), wn, "as_strided")
+    assert_bit_equal(al.to_numpy(w + w), wn + wn, "as_strided add")
+
+
+@pytest.mark.parametrize("shape,perm", [((64, 96), (1, 0)), ((5, 33, 70), (2, 1, 0)), ((5, 33, 70), (0, 2, 1)),
+                                        ((3, 40, 2, 50), (3, 2, 1, 0)), ((130, 257), (1, 0))])
+def test_transposed_tile_path(al, orc, rng, shape, perm):
+    x = rng.standard_normal(shape).astype(np.float32)
+    y = rng.standard_normal(tuple(shape[p] for p in perm)).astype(np.float32)
+    X, Y = al.from_numpy(x), al.from_numpy(y)
+    xt = X.transpose(perm)
+    assert xt.view
+    want = np.transpose(x, perm)
+    assert_bit_equal(al.to_numpy(xt + Y), want + y, "T + Y")
+    assert_bit_equal(al.to_numpy(al.copy(xt, deep=True)), want, "deep copy of T")
+    assert_bit_equal(al.to_numpy(xt.ravel()), want.reshape(-1), "ravel of T")
+    assert_bit_equal(al.to_numpy(al.sqrt(al.abs(xt))), np.sqrt(np.abs(want)), "unary of T")
+
+
+def test_general_fallback_equals_fast_paths(al, rng):
+    """force_general=1 routes everything through the scalar gather kernel; results must not move."""
+    from arraylib_b200._lib import lib
+    a = rng.standard_normal((9, 1, 64)).astype(np.float32)
+    b = rng.standard_normal((1, 11, 64)).astype(np.float32)
+    t = rng.standard_normal((64, 99)).astype(np.float32)
+    A, B, T = al.from_numpy(a), al.from_numpy(b), al.from_numpy(t)
+    fast = [al.to_numpy(A + B), al.to_numpy(al.copy(T.transpose((1, 0)), deep=True))]
+    assert lib.al_set_tuning(b"force_general", 1) == 0
+    try:
+        slow = [al.to_numpy(A + B), al.to_numpy(al.copy(T.transpose((1, 0)), deep=True))]
+        assert lib.al_last_kernel() == b"ew_nd_scalar"
+    finally:
+        lib.al_set_tuning(b"force_general", 0)
+    for f, s in zip(fast, slow):
+        assert_bit_equal(f, s, "fast vs general")
+
+
+@pytest.mark.parametrize("op", EXACT_UNARY)
+def test_unary_exact(al, orc, rng, op):
+    x = special_values(rng, (7, 129))
+    got = al.to_numpy(getattr(al, op)(al.from_numpy(x)))
+    assert_bit_equal(got, orc.unary(op, x), op)
+
+
+@pytest.mark.parametrize("op", LIBM_UNARY)
+def test_unary_libm_within_one_ulp(al, orc, rng, op):
+    """The reference rounds a double libm result to f32. Device FP64 libm is within
+    1-2 double ulp of glibc's, so the f32 results may differ by one f32 ulp on a ~2^-28 fraction of
+    inputs. Stated tolerance: <= 1 f32 ulp, and <= 1e-4 of the elements differ at all."""
+    x = (rng.standard_normal(1 << 16) * 3).astype(np.float32)
+    if op in ("asin", "acos", "atanh"):
+        x = np.tanh(x).astype(np.float32)
+    if op == "acosh":
+        x = (np.abs(x) + 1).astype(np.float32)
+    if op == "log":
+        x = np.abs(x).astype(np.float32) + np.float32(1e-3)
+    got = al.to_numpy(getattr(al, op)(al.from_numpy(x)))
+    want = orc.unary(op, x)
+    finite = np.isfinite(want)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ulp = np.abs(got[finite].view(np.int32).astype(np.int64) - want[finite].view(np.int32).astype(np.int64))
+    assert ulp.max() <= 1, f"{op}: max ulp {ulp.max()}"
+    assert (ulp != 0).mean() <= 1e-4, f"{op}: {(ulp != 0).mean():.2e} of elements differ"
+
+
+def test_where(al, orc, rng):
+    c = special_values(rng, (6, 50))
+    l, r = rng.standard_normal((6, 50)).astype(np.float32), rng.standard_normal((6, 50)).astype(np.float32)
+    C, L, R = al.from_numpy(c), al.from_numpy(l), al.from_numpy(r)
+    assert_bit_equal(al.to_numpy(al.where(C, L, R)), orc.where(c, l, r), "aaa")
+    assert_bit_equal(al.to_numpy(al.where(C, L, 2.0)), orc.where(c, l, 2.0), "aas")
+    assert_bit_equal(al.to_numpy(al.where(C, -1.0, R)), orc.where(c, -1.0, r), "asa")
+
+
+def test_reversed_scalar_operands(al, rng):
+    a = rng.standard_normal(100).astype(np.float32)
+    A = al.from_numpy(a)
+    assert_bit_equal(al.to_numpy(1.5 + A), np.float32(1.5) + a)
+    assert_bit_equal(al.to_numpy(1.5 - A), np.float32(1.5) - a)
+    assert_bit_equal(al.to_numpy(2.0 * A), np.float32(2) * a)
+    assert_bit_equal(al.to_numpy(2.0 / A), np.float32(2) / a)
+
+
+def test_errors_raise_instead_of_aborting(al):
+    a, b = al.ones((2, 3)), al.ones((4,))
+    with pytest.raises(AssertionError):
+        a + b
+    from arraylib_b200._lib import lib
+    assert not lib.array_array_sum(a.buffer, b.buffer)
+    assert lib.al_last_error().startswith(b"ValueError")
+    with pytest.raises(ValueError):
+        al.arange(10).as_strided(shape=(8, 4), stride=(1, 1))  # would read past the buffer
+    with pytest.raises(NotImplementedError):
+        al.apply(lambda v: v * v + 1.0, a)
+    assert not lib.array_op(None, a.buffer)
+    assert lib.al_last_error().startswith(b"NotImplementedError")

@@ -1,0 +1,188 @@
+"""GPU parity: reduce_sum / reduce_max / reduce_min over arbitrary dim sets.
+
+Tolerance for reduce_sum (the summation ORDER differs from the reference):
+  * small-integer inputs (every partial sum < 2^24): bit-exact, order cannot matter;
+  * general inputs, n reduced elements per output: |gpu - ref| <= 2 * n * 2^-24 * sum|x_i|;
+reduce_max / reduce_min are bit-exact.
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+from tests.conftest import assert_bit_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def power_set(items):
+    for r in range(len(items) + 1):
+        yield from itertools.combinations(items, r)
+
+
+def int_data(rng, shape):
+    return rng.integers(-8, 9, size=shape).astype(np.float32)
+
+
+def sum_tolerance(x, dims):
+    n = int(np.prod([x.shape[d] for d in dims])) if dims else 1
+    return 2.0 * n * 2.0 ** -24 * np.sum(np.abs(x.astype(np.float64)), axis=tuple(dims), keepdims=True)
+
+
+@pytest.mark.parametrize("dims", list(power_set((0, 1, 2, 3))))
+@pytest.mark.parametrize("op", ["sum", "max", "min"])
+def test_power_set_golden(al, orc, op, dims):
+    """The reference's own known-answer test: tests/test_array.py:222-252."""
+    a = al.arange(1, 361).reshape((3, 4, 5, 6))
+    x = np.arange(1, 361, dtype=np.float32).reshape(3, 4, 5, 6)
+    got = getattr(al, f"reduce_{op}")(a, dims=dims)
+    want = {"sum": np.sum, "max": np.max, "min": np.min}[op](x, axis=dims, keepdims=True)
+    assert got.shape == want.shape
+    assert_bit_equal(al.to_numpy(got), want, f"{op} {dims}")
+    assert_bit_equal(al.to_numpy(got), orc.reduce(op, x, dims), f"{op} {dims} vs oracle")
+
+
+SHAPES = [(7,), (1,), (5, 64), (64, 5), (3, 1, 9), (16, 33, 8), (4, 130, 3, 12), (2, 3, 4, 5, 6), (9, 4096), (4096, 9),
+          (6, 40, 40, 8), (100000,), (3, 70000), (70000, 3)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_integer_sums_bit_exact_all_dim_sets(al, orc, rng, shape):
+    x = int_data(rng, shape)
+    X = al.from_numpy(x)
+    for dims in power_set(tuple(range(len(shape)))):
+        want = orc.reduce("sum", x, dims)
+        got = al.reduce_sum(X, dims=dims)
+        assert got.shape == want.shape and not got.view
+        assert_bit_equal(al.to_numpy(got), want, f"sum {shape} {dims}")
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("op", ["max", "min"])
+def test_max_min_bit_exact(al, orc, rng, shape, op):
+    x = rng.standard_normal(shape).astype(np.float32)
+    x.reshape(-1)[:: 7] = np.nan  # fmax/fmin ignore NaN
+    if x.size > 3:
+        x.reshape(-1)[1] = np.inf
+        x.reshape(-1)[2] = -np.inf
+    X = al.from_numpy(x)
+    for dims in power_set(tuple(range(len(shape)))):
+        assert_bit_equal(al.to_numpy(getattr(al, f"reduce_{op}")(X, dims=dims)), orc.reduce(op, x, dims), f"{op} {dims}")
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_float_sums_within_stated_tolerance(al, orc, ref, rng, shape):
+    x = rng.standard_normal(shape).astype(np.float32)
+    X = al.from_numpy(x)
+    for dims in power_set(tuple(range(len(shape)))):
+        want = orc.reduce("sum", x, dims).astype(np.float64)
+        got = al.to_numpy(al.reduce_sum(X, dims=dims)).astype(np.float64)
+        tol = sum_tolerance(x, dims)
+        assert np.all(np.abs(got - want) <= tol), f"{shape} {dims}: max err {np.abs(got - want).max()}"
+        # and no worse than the reference relative to the exact (float64) sum
+        exact = np.sum(x.astype(np.float64), axis=dims, keepdims=True) if dims else x.astype(np.float64)
+        assert np.all(np.abs(got - exact) <= np.abs(want - exact) + 2.0 ** -22 * np.abs(exact) + tol * 0.5)
+
+
+def test_against_compiled_reference(al, ref, rng):
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    x = int_data(rng, (5, 6, 7, 8))
+    X, RX = al.from_numpy(x), ref.from_numpy(x)
+    for dims in power_set((0, 1, 2, 3)):
+        for op in ("sum", "max", "min"):
+            want = ref.reduce(op, RX, dims)
+            got = getattr(al, f"reduce_{op}")(X, dims=dims)
+            assert got.shape == want.shape and got.stride == want.stride
+            assert_bit_equal(al.to_numpy(got), want.numpy(), f"{op} {dims}")
+
+
+def test_strided_sources(al, orc, rng):
+    x = int_data(rng, (12, 20, 6))
+    X = al.from_numpy(x)
+    xt = np.transpose(x, (2, 0, 1))
+    XT = X.transpose((2, 0, 1))
+    assert XT.view
+    for dims in power_set((0, 1, 2)):
+        assert_bit_equal(al.to_numpy(al.reduce_sum(XT, dims=dims)), orc.reduce("sum", xt, dims), f"T {dims}")
+    v = X[2:12:3, 1:20:2, 0:6:1]
+    vn = x[2:12:3, 1:20:2, :]
+    for dims in power_set((0, 1, 2)):
+        assert_bit_equal(al.to_numpy(al.reduce_sum(v, dims=dims)), orc.reduce("sum", vn, dims), f"slice {dims}")
+
+
+@pytest.mark.parametrize("n,w", [(1 << 16, 64), (100003, 64), (5000, 8), (20000, 100), (70000, 1024), (300, 64)])
+def test_sliding_window_view(al, orc, rng, n, w):
+    """as_strided (n-w+1, w) with strides (1, 1), reduce over the window axis (config C5a)."""
+    base = int_data(rng, (n,))
+    B = al.from_numpy(base)
+    V = B.as_strided(shape=(n - w + 1, w), stride=(1, 1))
+    vn = np.lib.stride_tricks.as_strided(base, shape=(n - w + 1, w), strides=(4, 4))
+    got = al.reduce_sum(V, dims=[1])
+    assert got.shape == (n - w + 1, 1)
+    assert_bit_equal(al.to_numpy(got), orc.reduce("sum", vn, (1,)), "window ints")
+    assert_bit_equal(al.to_numpy(al.reduce_max(V, dims=[1])), orc.reduce("max", vn, (1,)), "window max")
+    # the transposed view (w, n-w+1) reduced over axis 0 is the same computation
+    VT = B.as_strided(shape=(w, n - w + 1), stride=(1, 1))
+    assert_bit_equal(al.to_numpy(al.reduce_sum(VT, dims=[0])).reshape(-1), orc.reduce("sum", vn, (1,)).reshape(-1), "wT")
+    f = rng.standard_normal(n).astype(np.float32)
+    F = al.from_numpy(f).as_strided(shape=(n - w + 1, w), stride=(1, 1))
+    fn_ = np.lib.stride_tricks.as_strided(f, shape=(n - w + 1, w), strides=(4, 4))
+    err = np.abs(al.to_numpy(al.reduce_sum(F, dims=[1])).astype(np.float64) - orc.reduce("sum", fn_, (1,)))
+    assert np.all(err <= sum_tolerance(fn_, (1,)))
+
+
+def test_window_kernel_matches_generic_path(al, rng):
+    from arraylib_b200._lib import lib
+    base = rng.standard_normal(50000).astype(np.float32)
+    V = al.from_numpy(base).as_strided(shape=(50000 - 63, 64), stride=(1, 1))
+    fast = al.to_numpy(al.reduce_max(V, dims=[1]))
+    assert lib.al_last_kernel() == b"reduce_window"
+    lib.al_set_tuning(b"disable_window", 1)
+    try:
+        slow = al.to_numpy(al.reduce_max(V, dims=[1]))
+        assert lib.al_last_kernel() != b"reduce_window"
+    finally:
+        lib.al_set_tuning(b"disable_window", 0)
+    assert_bit_equal(fast, slow, "window vs generic")
+
+
+@pytest.mark.parametrize("splits", [1, 2, 7, 64])
+def test_two_pass_split_is_consistent(al, orc, rng, splits):
+    from arraylib_b200._lib import lib
+    x = int_data(rng, (4, 5000, 16))
+    X = al.from_numpy(x)
+    lib.al_set_tuning(b"reduce_splits", splits)
+    try:
+        assert_bit_equal(al.to_numpy(al.reduce_sum(X, dims=(1,))), orc.reduce("sum", x, (1,)), "outer split")
+        assert_bit_equal(al.to_numpy(al.reduce_sum(X, dims=(0, 1, 2))), orc.reduce("sum", x, (0, 1, 2)), "full split")
+        assert_bit_equal(al.to_numpy(al.reduce_sum(X, dims=(1, 2))), orc.reduce("sum", x, (1, 2)), "inner split")
+    finally:
+        lib.al_set_tuning(b"reduce_splits", 0)
+
+
+def test_config4_shapes_reduced(al, orc, rng):
+    """[64,512,512,64] scaled to [8,64,64,64]: dims (1,2) and dims (3,) (config C4)."""
+    x = int_data(rng, (8, 64, 64, 64))
+    X = al.from_numpy(x)
+    a = al.reduce_sum(X, dims=(1, 2))
+    assert a.shape == (8, 1, 1, 64) and a.stride == (64, 64, 64, 1)
+    assert_bit_equal(al.to_numpy(a), orc.reduce("sum", x, (1, 2)), "C4a")
+    b = al.reduce_sum(X, dims=(3,))
+    assert b.shape == (8, 64, 64, 1)
+    assert_bit_equal(al.to_numpy(b), orc.reduce("sum", x, (3,)), "C4b")
+    c = al.reduce_sum(X, dims=(0,))
+    assert_bit_equal(al.to_numpy(c), orc.reduce("sum", x, (0,)), "C4 dim0")
+
+
+def test_reduce_with_callable_and_init(al, orc, rng):
+    x = int_data(rng, (3, 4, 5, 6))
+    X = al.from_numpy(x)
+    got = al.reduce(lambda acc, v: acc + v, X, dims=(1, 2), init=0)
+    assert_bit_equal(al.to_numpy(got), orc.reduce("sum", x, (1, 2)), "lambda sum")
+    got = al.reduce(max, X, dims=(0,), init=-100.0)
+    assert_bit_equal(al.to_numpy(got), orc.reduce("max", x, (0,), init=-100.0), "max init")
+    got = al.reduce(lambda a, b: a + b, X, dims=(3,), init=2.0)  # the reference folds init in twice
+    assert_bit_equal(al.to_numpy(got), orc.reduce("sum", x, (3,), init=2.0), "sum init 2")
+    with pytest.raises(NotImplementedError):
+        al.reduce(lambda a, b: a - b, X, dims=(0,))
