@@ -350,10 +350,11 @@ def host_buffer(shape):
     import numpy as np
 
     n = int(np.prod(shape)) if len(tuple(shape)) else 1
-    ptr = lib.al_host_alloc(max(n, 1) * 4)
+    n_alloc = n if n > 0 else 1  # (this module rebinds max/min/abs/pow to array ops)
+    ptr = lib.al_host_alloc(n_alloc * 4)
     if not ptr:
         raise_last_error()
-    raw = (C.c_float * max(n, 1)).from_address(ptr)
+    raw = (C.c_float * n_alloc).from_address(ptr)
     keeper = _PinnedOwner(ptr, raw)
     arr = np.frombuffer(keeper, dtype=np.float32, count=n).reshape(shape)
     return arr

@@ -31,9 +31,12 @@ struct Runtime {
     // tunables (al_set_tuning)
     long stream_store_min_bytes = 64l << 20;  // outputs at least this big use st.global.cs
     long ew_unroll = 4;
+    long load_policy = 0;      // streaming loads: 0 ld.global.cs, 1 ld.global.nc, 2 nc+L1::no_allocate
     long force_general = 0;    // 1: disable the vector / tile fast paths (tests the fallback)
     long reduce_splits = 0;    // 0 = auto
     long disable_window = 0;
+    long tile64 = 1;           // 0: use the 32x32 scalar transpose tile even when the float4 one applies
+    long outer_tile = 1;       // 0: do not use the register-tiled outer-broadcast kernel
 };
 Runtime& rt();
 bool ensure_init();  // lazily al_init(-1); false (with error set) on failure
@@ -62,6 +65,8 @@ inline void note_launch(const char* name) {
 bool check_launch(const char* name);  // cudaGetLastError after a launch
 
 // ---- storage ---------------------------------------------------------------------------------
+void* device_alloc(size_t bytes);  // cached cudaMalloc block; nullptr (error set) on failure
+void device_free(void* p);         // back to the cache (safe immediately: single-stream ordering)
 size_t count_of(const size_t* shape, size_t ndim);  // zero extents count as 1 (arraylib.c:66-72)
 NDArray* new_array(const size_t* shape, size_t ndim);  // contiguous, fresh device buffer
 NDArray* new_view(const NDArray* src, const size_t* shape, const size_t* stride, size_t ndim,

@@ -1,0 +1,21 @@
+// One slice of the elementwise engine's template instantiations (split so the slices compile in parallel).
+#include "elementwise.cuh"
+
+namespace al {
+
+template <template <int> class FT, int N, typename Make>
+static bool dispatch_op(int op, const EwCall& c, const Folded& fo, Make make) {
+    if constexpr (N == 0) {
+        set_error("ValueError: unknown op code %d", op);
+        return false;
+    } else {
+        if (op == N - 1) return run_functor(make(FT<N - 1>{}), c, fo);
+        return dispatch_op<FT, N - 1>(op, c, fo, make);
+    }
+}
+
+bool launch_ew_binary(const EwCall& c, const Folded& fo) {
+    return dispatch_op<BinF, AL_BINOP_COUNT>(c.op, c, fo, [](auto f) { return f; });
+}
+
+}  // namespace al

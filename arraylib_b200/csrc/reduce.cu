@@ -290,25 +290,105 @@ reduce_finish_kernel(const float* __restrict__ partial, float* __restrict__ out,
 }
 
 // ---- reduce_window: overlapping windows, out[i] = sum_{j<w} x[i+j] --------------------------------
-// Each CTA owns WT consecutive outputs and stages x[i0 .. i0+WT+w-2] in shared memory. The staged
-// span is cut into blocks of w; with P = inclusive prefix scan and S = inclusive suffix scan inside
-// each block, a window that starts at block offset k is S[k] (rest of its block) + P[k-1] of the
-// next block, i.e. 2 shared reads + 1 add per output instead of w reads (van Herk / Gil-Werman).
-// The per-block scans are done by one thread per block with stride-(w+1) padding so the 32 lanes of
-// a warp hit 32 different banks.
-constexpr int kWinThreads = 256;
+// Each CTA stages `span` consecutive source elements in shared memory and emits span - w outputs.
+// The staged span is cut into blocks of w; with P = inclusive prefix scan and S = inclusive suffix
+// scan inside each block, the window that starts at offset k of block b is
+//     S[b][k]  (rest of its own block)  (+)  P[b+1][k-1]  (head of the next block, k > 0)
+// i.e. 2 shared reads + 1 add per output instead of w reads (van Herk / Gil-Werman), and the
+// rounding behaviour is that of two sequential sums of <= w terms. Blocks are stored with a pitch
+// of w+1 floats so that threads scanning different blocks hit different banks.
+
+// Fixed-w variant (w = 8/16/32/64): the first half of the CTA's warps build the suffix scans, the
+// second half the prefix scans, each thread owning 64/W blocks held in registers.
+constexpr int kWinThreads = 256;      // generic-w kernel
+constexpr int kWinFixedThreads = 128; // fixed-w kernel: 128 threads x 32 elements = 4096-element span,
+constexpr int kWinLoads = 32;         // all 32 loads of a thread in flight at once; ~5 CTAs per SM
+
+template <int OP, int W>
+__global__ void __launch_bounds__(kWinFixedThreads)
+reduce_window_fixed_kernel(const float* __restrict__ x, float* __restrict__ out, uint32_t nout, float init) {
+    extern __shared__ float wsm[];
+    constexpr int kWinThreads = kWinFixedThreads, kWinSpan = kWinFixedThreads * kWinLoads;
+    constexpr int PITCH = W + 1, NBLK = kWinSpan / W, TILE = kWinSpan - W, PER_THREAD = 64 / W;
+    constexpr int SHIFT = W == 64 ? 6 : W == 32 ? 5 : W == 16 ? 4 : 3;
+    float* P = wsm;
+    float* S = wsm + NBLK * PITCH;
+    const size_t i0 = (size_t)blockIdx.x * TILE;
+    const size_t n_in = (size_t)nout + W - 1;
+    const int tid = threadIdx.x;
+    // stage: coalesced 4-byte loads, 16 in flight per thread; element e -> P[e/W][e%W]
+    {
+        float v[kWinLoads];
+#pragma unroll
+        for (int u = 0; u < kWinLoads; u++) {
+            const size_t gi = i0 + u * kWinThreads + tid;
+            v[u] = gi < n_in ? __ldcs(x + gi) : rident<OP>();
+        }
+#pragma unroll
+        for (int u = 0; u < kWinLoads; u++) {
+            const int e = u * kWinThreads + tid;
+            P[(e >> SHIFT) * PITCH + (e & (W - 1))] = v[u];
+        }
+    }
+    __syncthreads();
+    const bool prefix_role = tid >= kWinThreads / 2;  // warp-uniform
+    const int owner = tid & (kWinThreads / 2 - 1);
+    float xr[PER_THREAD][W];
+#pragma unroll
+    for (int m = 0; m < PER_THREAD; m++) {
+        const float* p = P + (owner * PER_THREAD + m) * PITCH;
+#pragma unroll
+        for (int k = 0; k < W; k++) xr[m][k] = p[k];
+    }
+    __syncthreads();  // every block is in registers before P is overwritten in place
+#pragma unroll
+    for (int m = 0; m < PER_THREAD; m++) {
+        const int b = owner * PER_THREAD + m;
+        if (prefix_role) {
+            float* p = P + b * PITCH;
+            float run = xr[m][0];
+#pragma unroll
+            for (int k = 1; k < W; k++) {
+                run = racc<OP>(run, xr[m][k]);
+                p[k] = run;
+            }
+        } else {
+            float* sfx = S + b * PITCH;
+            float run = xr[m][W - 1];
+            sfx[W - 1] = run;
+#pragma unroll
+            for (int k = W - 2; k >= 0; k--) {
+                run = racc<OP>(xr[m][k], run);
+                sfx[k] = run;
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int e = tid; e < TILE; e += kWinThreads) {
+        const size_t gi = i0 + e;
+        if (gi < nout) {
+            const int b = e >> SHIFT, k = e & (W - 1);
+            float v = S[b * PITCH + k];
+            if (k) v = racc<OP>(v, P[(b + 1) * PITCH + k - 1]);
+            __stcs(out + gi, rfinal<OP>(init, v));
+        }
+    }
+}
+
+// Any-w variant: one thread scans one block serially.
 template <int OP>
 __global__ void __launch_bounds__(kWinThreads)
 reduce_window_kernel(const float* __restrict__ x, float* __restrict__ out, uint32_t nout, uint32_t w, uint32_t nblk,
                      float init) {
     extern __shared__ float wsm[];
-    const uint32_t pitch = w + 1;               // padded block pitch
-    float* P = wsm;                             // [nblk+1][pitch] prefix scans
+    const uint32_t pitch = w + 1;
+    float* P = wsm;                               // [nblk+1][pitch] prefix scans
     float* S = wsm + (size_t)(nblk + 1) * pitch;  // [nblk+1][pitch] suffix scans
-    const uint32_t tile = nblk * w;             // outputs per CTA
+    const uint32_t tile = nblk * w;               // outputs per CTA
     const size_t i0 = (size_t)blockIdx.x * tile;
-    const size_t n_in = (size_t)nout + w - 1;   // valid source elements
-    const uint32_t span = tile + w;             // staged elements (one extra block covers the halo)
+    const size_t n_in = (size_t)nout + w - 1;
+    const uint32_t span = tile + w;
     for (uint32_t e = threadIdx.x; e < span; e += kWinThreads) {
         const size_t gi = i0 + e;
         const float v = gi < n_in ? __ldcs(x + gi) : rident<OP>();
@@ -340,6 +420,24 @@ reduce_window_kernel(const float* __restrict__ x, float* __restrict__ out, uint3
         if (k) v = racc<OP>(v, P[(b + 1) * pitch + k - 1]);
         __stcs(out + gi, rfinal<OP>(init, v));
     }
+}
+
+template <int OP, int W>
+static bool launch_window_fixed(const float* src, float* out, uint32_t nout, float init) {
+    constexpr int kWinSpan = kWinFixedThreads * kWinLoads;
+    constexpr int TILE = kWinSpan - W;
+    const size_t smem = 2ull * (kWinSpan / W) * (W + 1) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        if (!cuda_ok(cudaFuncSetAttribute(reduce_window_fixed_kernel<OP, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                     "cudaFuncSetAttribute"))
+            return false;
+        configured = true;
+    }
+    const unsigned blocks = (unsigned)(((uint64_t)nout + TILE - 1) / TILE);
+    reduce_window_fixed_kernel<OP, W><<<blocks, kWinFixedThreads, smem, rt().stream>>>(src, out, nout, init);
+    note_launch("reduce_window");
+    return check_launch("reduce_window");
 }
 
 // ---- host planning ------------------------------------------------------------------------------------
@@ -393,6 +491,13 @@ static bool run_reduce(const float* src, float* out, const AxisList& K, const Ax
     if (!general && !r.disable_window && K.n == 1 && R.n == 1 && K.stride[0] == 1 && R.stride[0] == 1 &&
         R.extent[0] >= 8 && R.extent[0] <= 1024 && nout >= 4 * R.extent[0]) {
         const uint32_t w = (uint32_t)R.extent[0];
+        switch (w) {
+            case 8: return launch_window_fixed<OP, 8>(src, out, (uint32_t)nout, init);
+            case 16: return launch_window_fixed<OP, 16>(src, out, (uint32_t)nout, init);
+            case 32: return launch_window_fixed<OP, 32>(src, out, (uint32_t)nout, init);
+            case 64: return launch_window_fixed<OP, 64>(src, out, (uint32_t)nout, init);
+            default: break;
+        }
         uint32_t nblk = 8192 / w;  // ~8K outputs per CTA
         if (nblk < 1) nblk = 1;
         size_t smem = 2ull * (nblk + 1) * (w + 1) * sizeof(float);
@@ -438,7 +543,14 @@ static bool run_reduce(const float* src, float* out, const AxisList& K, const Ax
             a.kdiv[d] = make_fastdiv(a.kext[d] ? a.kext[d] : 1);
             a.rdiv[d] = make_fastdiv(a.rext[d] ? a.rext[d] : 1);
         }
-        const unsigned TY = rtot >= 64 ? 8 : 1, TX = 256 / TY;
+        // TX lanes along the kept axis (no wider than the kept extent), the rest of the CTA along
+        // the reduced axis
+        unsigned TX = 256, TY = 1;
+        if (rtot >= 64) {
+            TX = pow2_ceil(a.nk_items);
+            if (TX > 32) TX = 32;
+            TY = 256 / TX;
+        }
         const unsigned gx = (a.nk_items + TX - 1) / TX;
         unsigned splits = 1;
         if (r.reduce_splits > 0) splits = (unsigned)r.reduce_splits;
@@ -450,7 +562,8 @@ static bool run_reduce(const float* src, float* out, const AxisList& K, const Ax
         splits = (unsigned)((rtot + a.r_per_split - 1) / a.r_per_split);
         a.finalize = splits == 1;
         if (splits > 1) {
-            if (!cuda_ok(cudaMallocAsync((void**)&partial, (size_t)splits * nout * sizeof(float), st), "cudaMallocAsync(partials)")) return false;
+            partial = (float*)device_alloc((size_t)splits * nout * sizeof(float));
+            if (!partial) return false;
             a.dst = partial;
         } else {
             a.dst = out;
@@ -465,7 +578,7 @@ static bool run_reduce(const float* src, float* out, const AxisList& K, const Ax
             unsigned fb = nout <= 2048 ? (unsigned)((nout * 32 + 255) / 256) : (unsigned)((nout + 255) / 256);
             reduce_finish_kernel<OP><<<fb, 256, 0, st>>>(partial, out, (uint32_t)nout, splits, init);
             note_launch("reduce_finish");
-            cudaFreeAsync(partial, st);
+            device_free(partial);
             return check_launch("reduce_finish");
         }
         return true;
@@ -499,7 +612,8 @@ static bool run_reduce(const float* src, float* out, const AxisList& K, const Ax
     splits = (a.nr_items + a.r_per_split - 1) / a.r_per_split;
     a.finalize = splits == 1;
     if (splits > 1) {
-        if (!cuda_ok(cudaMallocAsync((void**)&partial, (size_t)splits * nout * sizeof(float), st), "cudaMallocAsync(partials)")) return false;
+        partial = (float*)device_alloc((size_t)splits * nout * sizeof(float));
+        if (!partial) return false;
         a.dst = partial;
     } else {
         a.dst = out;
@@ -534,7 +648,7 @@ static bool run_reduce(const float* src, float* out, const AxisList& K, const Ax
         unsigned fb = nout <= 2048 ? (unsigned)((nout * 32 + 255) / 256) : (unsigned)((nout + 255) / 256);
         reduce_finish_kernel<OP><<<fb, 256, 0, st>>>(partial, out, (uint32_t)nout, splits, init);
         note_launch("reduce_finish");
-        cudaFreeAsync(partial, st);
+        device_free(partial);
         return check_launch("reduce_finish");
     }
     return true;

@@ -22,6 +22,9 @@ SHAPE_PAIRS = [
     ((5, 1, 7), (3, 1)), ((8, 1, 64), (1, 8, 64)), ((8, 8, 64), (64,)), ((3, 4, 5, 6), (5, 1)),
     ((33, 1, 1, 36), (1, 7, 1, 36)), ((2, 3, 4, 5, 6), (4, 1, 6)), ((1024,), (1024,)), ((1031,), (1031,)),
     ((257, 129), (129,)), ((16, 4096), (16, 1)),
+    # outer-broadcast (register-tiled) plan: ragged block edges, batch axes, inner broadcast
+    ((6, 1, 5, 8), (1, 9, 1, 8)), ((4, 5, 1, 16), (4, 1, 7, 16)), ((9, 1, 1), (1, 10, 8)), ((1, 13, 12), (11, 1, 12)),
+    ((2, 3, 1, 6, 1, 4), (1, 1, 5, 1, 7, 4)), ((64, 1, 256), (1, 48, 256)),
 ]
 
 
@@ -123,6 +126,48 @@ def test_transposed_tile_path(al, orc, rng, shape, perm):
     assert_bit_equal(al.to_numpy(al.copy(xt, deep=True)), want, "deep copy of T")
     assert_bit_equal(al.to_numpy(xt.ravel()), want.reshape(-1), "ravel of T")
     assert_bit_equal(al.to_numpy(al.sqrt(al.abs(xt))), np.sqrt(np.abs(want)), "unary of T")
+
+
+@pytest.mark.parametrize("shape,perm", [((128, 192), (1, 0)), ((3, 64, 2, 52), (0, 3, 2, 1)), ((8, 260, 68), (0, 2, 1)),
+                                        ((4, 100, 36), (0, 2, 1))])
+def test_tile64_equals_tile32(al, rng, shape, perm):
+    """Shapes whose extents are multiples of 4 take the 128-bit transpose tile; the scalar 32x32
+    tile must give the same bits."""
+    from arraylib_b200._lib import lib
+    x = rng.standard_normal(shape).astype(np.float32)
+    y = rng.standard_normal(tuple(shape[p] for p in perm)).astype(np.float32)
+    X, Y = al.from_numpy(x), al.from_numpy(y)
+    wide = [al.to_numpy(X.transpose(perm) - Y), al.to_numpy(al.copy(X.transpose(perm), deep=True))]
+    assert lib.al_last_kernel() == b"ew_tile64_transpose"
+    lib.al_set_tuning(b"tile64", 0)
+    try:
+        narrow = [al.to_numpy(X.transpose(perm) - Y), al.to_numpy(al.copy(X.transpose(perm), deep=True))]
+        assert lib.al_last_kernel() == b"ew_tile_transpose"
+    finally:
+        lib.al_set_tuning(b"tile64", 1)
+    for wv, nv, ref_ in zip(wide, narrow, [np.transpose(x, perm) - y, np.transpose(x, perm)]):
+        assert_bit_equal(wv, nv, "tile64 vs tile32")
+        assert_bit_equal(wv, ref_, "tile64 vs numpy")
+
+
+def test_outer_broadcast_plan_is_used_and_exact(al, orc, rng):
+    from arraylib_b200._lib import lib
+    a = rng.standard_normal((37, 1, 64)).astype(np.float32)
+    b = rng.standard_normal((1, 29, 64)).astype(np.float32)
+    A, B = al.from_numpy(a), al.from_numpy(b)
+    for op in ("sub", "div", "pow", "gt"):
+        got = al.to_numpy(getattr(al, op)(A, B))
+        assert lib.al_last_kernel() == b"ew_outer_bcast"
+        assert_bit_equal(got, orc.binary(op, a, b), op)
+        got = al.to_numpy(getattr(al, op)(B, A))  # operand roles swapped
+        assert_bit_equal(got, orc.binary(op, b, a), op + " swapped")
+    lib.al_set_tuning(b"outer_tile", 0)
+    try:
+        plain = al.to_numpy(A - B)
+        assert lib.al_last_kernel() == b"ew_nd_vec4"
+    finally:
+        lib.al_set_tuning(b"outer_tile", 1)
+    assert_bit_equal(plain, a - b, "nd kernel")
 
 
 def test_general_fallback_equals_fast_paths(al, rng):

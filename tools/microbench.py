@@ -1,0 +1,109 @@
+"""Development microbenchmarks (not part of the product or the bench contract): times single ops
+with CUDA events on the library stream under different tuning knobs. Usage under gpurun:
+    python tools/microbench.py [fill|ew|bcast|transpose|window|reduce ...]
+"""
+import ctypes as C
+import statistics
+import sys
+import os
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+import arraylib as al  # noqa: E402
+from arraylib_b200._lib import lib  # noqa: E402
+
+
+def tune(**kw):
+    for k, v in kw.items():
+        assert lib.al_set_tuning(k.encode(), int(v)) == 0, lib.al_last_error()
+
+
+def timed(fn, nbytes, label, reps=7, warm=2):
+    for _ in range(warm):
+        r = fn()
+        del r
+    ts = []
+    for i in range(reps):
+        lib.al_event_record(0)
+        r = fn()
+        lib.al_event_record(1)
+        ms = C.c_float()
+        assert lib.al_event_elapsed(0, 1, C.byref(ms)) == 0
+        ts.append(ms.value)
+        del r
+    med = statistics.median(ts)
+    print(f"{label:58s} {med:8.4f} ms  {nbytes / med / 1e6:8.1f} GB/s  (min {min(ts):.4f})  [{lib.al_last_kernel().decode()}]", flush=True)
+    return med
+
+
+def rnd(shape, seed=0):
+    n = int(np.prod(shape))
+    blk = np.random.default_rng(seed).standard_normal(min(n, 1 << 22), dtype=np.float32)
+    return al.from_numpy(np.resize(blk, n).reshape(shape))
+
+
+def bench_fill():
+    for gib in (1, 4):
+        n = gib << 28
+        timed(lambda: al.full((n,), 1.5), 4 * n, f"fill_const {gib} GiB (write only)")
+
+
+def bench_ew():
+    n = 1 << 28
+    a, b = rnd((n,), 1), rnd((n,), 2)
+    for unroll in (1, 2, 4, 8):
+        for pol in (0, 1, 2):
+            for ss in (0, 1 << 62):
+                tune(ew_unroll=unroll, load_policy=pol, stream_store_min_bytes=ss)
+                timed(lambda: a + b, 12 * n, f"a+b 2^28 unroll={unroll} load_policy={pol} stream_store={'on' if ss == 0 else 'off'}", reps=5)
+    tune(ew_unroll=4, load_policy=0, stream_store_min_bytes=64 << 20)
+    timed(lambda: a + 1.0, 8 * n, "a+1.0 2^28")
+    timed(lambda: al.copy(a, deep=True), 8 * n, "deep copy 2^28 (contiguous)")
+
+
+def bench_bcast():
+    A, B, c = rnd((1024, 1, 4096), 1), rnd((1, 1024, 4096), 2), rnd((4096,), 3)
+    out = 1 << 32
+    for unroll in (2, 4, 8):
+        for ss in (0, 1 << 62):
+            tune(ew_unroll=unroll, stream_store_min_bytes=ss)
+            timed(lambda: A + B, 4 * out + 8 * (1 << 22), f"[1024,1,4096]+[1,1024,4096] unroll={unroll} stream_store={'on' if ss == 0 else 'off'}", reps=5)
+    tune(ew_unroll=4, stream_store_min_bytes=64 << 20)
+    t = A + B
+    timed(lambda: t + c, 8 * out, "t[1024,1024,4096] + c[4096]", reps=5)
+
+
+def bench_transpose():
+    m = 16384
+    X, Y = rnd((m, m), 1), rnd((m, m), 2)
+    timed(lambda: X.transpose((1, 0)) + Y, 12 * m * m, "X.T + Y 16384^2")
+    timed(lambda: X.transpose((1, 0)).reshape((m * m,)), 8 * m * m, "X.T.reshape (strided copy) 16384^2")
+    tune(force_general=1)
+    timed(lambda: X.transpose((1, 0)) + Y, 12 * m * m, "X.T + Y 16384^2 (scalar gather fallback)", reps=3)
+    tune(force_general=0)
+
+
+def bench_window():
+    n, w = 1 << 28, 64
+    base = rnd((n,), 1)
+    timed(lambda: base.as_strided(shape=(n - w + 1, w), stride=(1, 1)).reduce_sum(dims=[1]), 4 * n + 4 * (n - w + 1), "window-64 reduce_sum 2^28")
+    n2 = 1 << 24
+    b2 = rnd((n2,), 1)
+    tune(disable_window=1)
+    timed(lambda: b2.as_strided(shape=(n2 - w + 1, w), stride=(1, 1)).reduce_sum(dims=[1]), 8 * n2, "window-64 reduce_sum 2^24 generic path", reps=3)
+    tune(disable_window=0)
+
+
+def bench_reduce():
+    X = rnd((64, 512, 512, 64), 1)
+    n = 1 << 30
+    for dims in ((1, 2), (3,), (0,), (0, 1, 2, 3), (0, 1, 2), (2, 3), (1,)):
+        timed(lambda: X.reduce_sum(dims=dims), 4 * n, f"reduce_sum [64,512,512,64] dims={dims}")
+    timed(lambda: X.reduce_max(dims=(1, 2)), 4 * n, "reduce_max dims=(1,2)")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["fill", "ew", "bcast", "transpose", "window", "reduce"]
+    for w in which:
+        globals()[f"bench_{w}"]()
