@@ -338,6 +338,7 @@ template <typename F>
 __global__ void __launch_bounds__(256) ew_tile64_kernel(const TileArgs<F::NIN> a, const F f) {
     constexpr int NIN = F::NIN;
     __shared__ float4 tile[NIN][kT64 * 16];
+    // (A grouped 8x8 CTA order was measured and gave no gain over this q-fastest order.)
     uint32_t t = blockIdx.x;
     uint32_t r = fdiv(t, a.div_tq);
     const uint32_t tq = t - r * a.tiles_q;

@@ -304,35 +304,50 @@ constexpr int kWinThreads = 256;      // generic-w kernel
 constexpr int kWinFixedThreads = 128; // fixed-w kernel: 128 threads x 32 elements = 4096-element span,
 constexpr int kWinLoads = 32;         // all 32 loads of a thread in flight at once; ~5 CTAs per SM
 
+// With the default init (the op's identity) the reference's double init fold collapses: for sum it
+// only turns a -0 result into +0 (0 + (0 + v)), for max/min/prod it is the identity.
+template <int OP>
+__device__ __forceinline__ float rfinal_fast(float init, float v, bool init_is_identity) {
+    if (!init_is_identity) return rfinal<OP>(init, v);
+    if constexpr (OP == AL_RSUM) return __fadd_rn(v, 0.0f);
+    else return v;
+}
+
 template <int OP, int W>
 __global__ void __launch_bounds__(kWinFixedThreads)
-reduce_window_fixed_kernel(const float* __restrict__ x, float* __restrict__ out, uint32_t nout, float init) {
+reduce_window_fixed_kernel(const float* __restrict__ x, float* __restrict__ out, uint32_t nout, float init,
+                           int init_is_identity) {
     extern __shared__ float wsm[];
-    constexpr int kWinThreads = kWinFixedThreads, kWinSpan = kWinFixedThreads * kWinLoads;
-    constexpr int PITCH = W + 1, NBLK = kWinSpan / W, TILE = kWinSpan - W, PER_THREAD = 64 / W;
+    constexpr int T = kWinFixedThreads, SPAN = kWinFixedThreads * kWinLoads;
+    constexpr int PITCH = W + 1, NBLK = SPAN / W, TILE = SPAN - W, PER_THREAD = 64 / W;
     constexpr int SHIFT = W == 64 ? 6 : W == 32 ? 5 : W == 16 ? 4 : 3;
+    constexpr int BLK_PER_ROUND = T / W;  // blocks covered by one sweep of the CTA over consecutive elements
     float* P = wsm;
     float* S = wsm + NBLK * PITCH;
     const size_t i0 = (size_t)blockIdx.x * TILE;
     const size_t n_in = (size_t)nout + W - 1;
     const int tid = threadIdx.x;
-    // stage: coalesced 4-byte loads, 16 in flight per thread; element e -> P[e/W][e%W]
+    // Element e = u*T + tid lives at P[(e / W) * PITCH + e % W]; since W divides T, e % W is a
+    // per-thread constant and e / W advances by T/W per round, so every shared address below is
+    // `lane base + compile-time offset`.
+    const int kk = tid & (W - 1);
+    float* const stage = P + (tid >> SHIFT) * PITCH + kk;
     {
         float v[kWinLoads];
+        const float* src = x + i0 + tid;
+        if (i0 + SPAN <= n_in) {  // CTA-uniform fast path: no per-element bounds checks
 #pragma unroll
-        for (int u = 0; u < kWinLoads; u++) {
-            const size_t gi = i0 + u * kWinThreads + tid;
-            v[u] = gi < n_in ? __ldcs(x + gi) : rident<OP>();
+            for (int u = 0; u < kWinLoads; u++) v[u] = __ldcs(src + u * T);
+        } else {
+#pragma unroll
+            for (int u = 0; u < kWinLoads; u++) v[u] = (i0 + u * T + tid < n_in) ? __ldcs(src + u * T) : rident<OP>();
         }
 #pragma unroll
-        for (int u = 0; u < kWinLoads; u++) {
-            const int e = u * kWinThreads + tid;
-            P[(e >> SHIFT) * PITCH + (e & (W - 1))] = v[u];
-        }
+        for (int u = 0; u < kWinLoads; u++) stage[u * BLK_PER_ROUND * PITCH] = v[u];
     }
     __syncthreads();
-    const bool prefix_role = tid >= kWinThreads / 2;  // warp-uniform
-    const int owner = tid & (kWinThreads / 2 - 1);
+    const bool prefix_role = tid >= T / 2;  // warp-uniform
+    const int owner = tid & (T / 2 - 1);
     float xr[PER_THREAD][W];
 #pragma unroll
     for (int m = 0; m < PER_THREAD; m++) {
@@ -364,14 +379,29 @@ reduce_window_fixed_kernel(const float* __restrict__ x, float* __restrict__ out,
         }
     }
     __syncthreads();
-#pragma unroll 8
-    for (int e = tid; e < TILE; e += kWinThreads) {
-        const size_t gi = i0 + e;
-        if (gi < nout) {
-            const int b = e >> SHIFT, k = e & (W - 1);
-            float v = S[b * PITCH + k];
-            if (k) v = racc<OP>(v, P[(b + 1) * PITCH + k - 1]);
-            __stcs(out + gi, rfinal<OP>(init, v));
+    // output e = u*T + tid: S[b][kk] (+) P[b+1][kk-1], b = u*T/W + tid/W
+    const float* const s_lane = S + (tid >> SHIFT) * PITCH + kk;
+    const float* const p_lane = P + ((tid >> SHIFT) + 1) * PITCH + kk - 1;
+    float* dst = out + i0 + tid;
+    const bool has_head = kk != 0;
+    const bool ident = init_is_identity != 0;
+    if (i0 + TILE <= nout) {
+#pragma unroll
+        for (int u = 0; u < kWinLoads; u++) {
+            if (u * T + tid < TILE) {  // only the last round is partial (TILE = SPAN - W)
+                float v = s_lane[u * BLK_PER_ROUND * PITCH];
+                if (has_head) v = racc<OP>(v, p_lane[u * BLK_PER_ROUND * PITCH]);
+                __stcs(dst + u * T, rfinal_fast<OP>(init, v, ident));
+            }
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < kWinLoads; u++) {
+            if (u * T + tid < TILE && i0 + u * T + tid < nout) {
+                float v = s_lane[u * BLK_PER_ROUND * PITCH];
+                if (has_head) v = racc<OP>(v, p_lane[u * BLK_PER_ROUND * PITCH]);
+                __stcs(dst + u * T, rfinal_fast<OP>(init, v, ident));
+            }
         }
     }
 }
@@ -424,6 +454,8 @@ reduce_window_kernel(const float* __restrict__ x, float* __restrict__ out, uint3
 
 template <int OP, int W>
 static bool launch_window_fixed(const float* src, float* out, uint32_t nout, float init) {
+    const float ident_tab[AL_REDOP_COUNT] = {0.0f, -INFINITY, INFINITY, 1.0f};
+    const int init_is_identity = memcmp(&init, &ident_tab[OP], sizeof(float)) == 0;
     constexpr int kWinSpan = kWinFixedThreads * kWinLoads;
     constexpr int TILE = kWinSpan - W;
     const size_t smem = 2ull * (kWinSpan / W) * (W + 1) * sizeof(float);
@@ -435,7 +467,7 @@ static bool launch_window_fixed(const float* src, float* out, uint32_t nout, flo
         configured = true;
     }
     const unsigned blocks = (unsigned)(((uint64_t)nout + TILE - 1) / TILE);
-    reduce_window_fixed_kernel<OP, W><<<blocks, kWinFixedThreads, smem, rt().stream>>>(src, out, nout, init);
+    reduce_window_fixed_kernel<OP, W><<<blocks, kWinFixedThreads, smem, rt().stream>>>(src, out, nout, init, init_is_identity);
     note_launch("reduce_window");
     return check_launch("reduce_window");
 }
