@@ -108,6 +108,47 @@ def reduce_sharded(array, op: str = "sum", dims=None):
     return part
 
 
+def scatter_from_numpy(global_array):
+    """Upload this rank's leading-axis block of a host array that every rank holds in full."""
+    from . import core
+
+    lo, hi = shard_bounds(global_array.shape[0], _state["rank"], _state["world"])
+    return core.from_numpy(global_array[lo:hi])
+
+
+def window_shard_from_numpy(base, window: int):
+    """Upload the slice of a 1-D base buffer this rank needs for its share of the stride-1 sliding
+    windows of length `window` (own outputs + halo), and return (array, n_local_outputs)."""
+    from . import core
+
+    n_out = base.shape[0] - window + 1
+    lo, hi = window_halo_bounds(n_out, window, _state["rank"], _state["world"])
+    return core.from_numpy(base[lo:hi]), hi - lo - window + 1
+
+
+def allgather(shard):
+    """Concatenate equal-sized leading-axis shards on every rank (NCCL allgather)."""
+    from . import core
+    from ._lib import check_rc, lib
+
+    if _state["world"] == 1:
+        return shard
+    src = shard
+    if src.stride != tuple(_row_major(src.shape)):
+        src = core.copy(src, deep=True)
+    full = core.zeros((src.shape[0] * _state["world"],) + tuple(src.shape[1:]))
+    check_rc(lib.al_comm_allgather(src.buffer, full.buffer))
+    return full
+
+
+def _row_major(shape):
+    out, run = [], 1
+    for e in reversed(shape):
+        out.append(run)
+        run *= e
+    return tuple(reversed(out))
+
+
 def destroy() -> None:
     from ._lib import lib
 
