@@ -277,15 +277,16 @@ def run_gpu(args):
         v["frac_of_peak"] = round(v["gbs"] / peak, 3)
         v["pct_of_8TBs"] = round(100 * v["gbs"] / NOMINAL_GBS, 1)
 
-    # dominant kernel: the vectorised broadcast-add kernel (ew_nd_vec4<add>): c2_add + both C3 adds
-    dom = ["c2_add", "c3_bcast_add", "c3_bcast_add_vec"]
+    # dominant kernel by time: ew_nd_kernel<VEC=4, UNROLL=4, BinF<AL_SUM>>, launched by c2_add
+    # (contiguous) and c3_bcast_add_vec (row-broadcast); together ~45% of the step.
+    dom = ["c2_add", "c3_bcast_add_vec"]
     dom_ms = sum(per_op[n]["ms"] for n in dom) / len(dom)
     dom_bytes = sum(nbytes[n] for n in dom) / len(dom)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("ew_nd_vec4_add_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "ew_nd_kernel<VEC=4, BinF<AL_SUM>> (c2_add, c3_bcast_add, c3_bcast_add_vec)",
+    roofline = {"bound": "hbm", "kernel": "ew_nd_kernel<VEC=4, UNROLL=4, BinF<AL_SUM>> (launched by c2_add and c3_bcast_add_vec)",
                 "achieved": round(dom_bytes / (dom_ms * 1e-3) / 1e9, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": round(dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, 3), "traffic": traffic,
                 "algorithmic_bytes_per_launch": int(dom_bytes), "avg_launch_ms": round(dom_ms, 4), "launches_per_step": len(dom)}
@@ -334,7 +335,7 @@ def run_gpu(args):
         dist.destroy()
         tdist.destroy_process_group()
     if rank != 0:
-        return
+        return None
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -346,7 +347,7 @@ def run_gpu(args):
         "pct_of_8TBs_per_gpu": round(100 * value / world / NOMINAL_GBS, 1),
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "ops": per_op, "e2e": e2e, "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line))
+    return line
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -440,7 +441,7 @@ def reference_sample(steps: int, warmup: int):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     r = reference_sample(args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(r["value"], 3), "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -450,7 +451,27 @@ def run_reference(args):
         "cpu_baseline": r["cpu_baseline"],
         "e2e": {"value": round(r["value"], 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    return line
+
+
+class StdoutGuard:
+    """NCCL (and anything else) may print to fd 1; the contract is ONE JSON line on stdout. Route
+    fd 1 to stderr for the duration of the run and keep the real stdout for the final line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text: str):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
 
 
 def main():
@@ -463,10 +484,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_gpu(args)
+    with StdoutGuard() as out:
+        line = run_reference(args) if args.impl == "reference" else run_gpu(args)
+        if line is not None:
+            out.emit(json.dumps(line))
 
 
 if __name__ == "__main__":
