@@ -35,6 +35,7 @@ struct Runtime {
     long force_general = 0;    // 1: disable the vector / tile fast paths (tests the fallback)
     long reduce_splits = 0;    // 0 = auto
     long disable_window = 0;
+    long window_ctas_per_sm = 0;  // 0 = default (16 CTAs per SM, 4 of them resident)
     long tile64 = 1;           // 0: use the 32x32 scalar transpose tile even when the float4 one applies
     long outer_tile = 1;       // 0: do not use the register-tiled outer-broadcast kernel
 };

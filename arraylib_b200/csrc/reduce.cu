@@ -314,9 +314,9 @@ __device__ __forceinline__ float rfinal_fast(float init, float v, bool init_is_i
 }
 
 template <int OP, int W>
-__global__ void __launch_bounds__(kWinFixedThreads)
-reduce_window_fixed_kernel(const float* __restrict__ x, float* __restrict__ out, uint32_t nout, float init,
-                           int init_is_identity) {
+__global__ void __launch_bounds__(kWinFixedThreads, 4)
+reduce_window_fixed_kernel(const float* __restrict__ x, float* __restrict__ out, uint32_t nout, uint32_t n_tiles,
+                           float init, int init_is_identity) {
     extern __shared__ float wsm[];
     constexpr int T = kWinFixedThreads, SPAN = kWinFixedThreads * kWinLoads;
     constexpr int PITCH = W + 1, NBLK = SPAN / W, TILE = SPAN - W, PER_THREAD = 64 / W;
@@ -324,16 +324,25 @@ reduce_window_fixed_kernel(const float* __restrict__ x, float* __restrict__ out,
     constexpr int BLK_PER_ROUND = T / W;  // blocks covered by one sweep of the CTA over consecutive elements
     float* P = wsm;
     float* S = wsm + NBLK * PITCH;
-    const size_t i0 = (size_t)blockIdx.x * TILE;
     const size_t n_in = (size_t)nout + W - 1;
     const int tid = threadIdx.x;
-    // Element e = u*T + tid lives at P[(e / W) * PITCH + e % W]; since W divides T, e % W is a
-    // per-thread constant and e / W advances by T/W per round, so every shared address below is
+    // Element e = u*T + tid of a tile lives at P[(e / W) * PITCH + e % W]; since W divides T, e % W is
+    // a per-thread constant and e / W advances by T/W per round, so every shared address below is
     // `lane base + compile-time offset`.
     const int kk = tid & (W - 1);
     float* const stage = P + (tid >> SHIFT) * PITCH + kk;
-    {
-        float v[kWinLoads];
+    const float* const s_lane = S + (tid >> SHIFT) * PITCH + kk;
+    const float* const p_lane = P + ((tid >> SHIFT) + 1) * PITCH + kk - 1;
+    const bool prefix_role = tid >= T / 2;  // warp-uniform
+    const int owner = tid & (T / 2 - 1);
+    const bool has_head = kk != 0;
+    const bool ident = init_is_identity != 0;
+
+    // Persistent CTA: the loads of tile k+1 are issued right after tile k has been parked in shared
+    // memory, so they are in flight during the whole scan/emit work of tile k.
+    float v[kWinLoads];
+    auto fetch = [&](uint32_t tile) {
+        const size_t i0 = (size_t)tile * TILE;
         const float* src = x + i0 + tid;
         if (i0 + SPAN <= n_in) {  // CTA-uniform fast path: no per-element bounds checks
 #pragma unroll
@@ -342,67 +351,68 @@ reduce_window_fixed_kernel(const float* __restrict__ x, float* __restrict__ out,
 #pragma unroll
             for (int u = 0; u < kWinLoads; u++) v[u] = (i0 + u * T + tid < n_in) ? __ldcs(src + u * T) : rident<OP>();
         }
+    };
+    uint32_t tile = blockIdx.x;
+    if (tile < n_tiles) fetch(tile);
+    for (; tile < n_tiles; tile += gridDim.x) {
 #pragma unroll
         for (int u = 0; u < kWinLoads; u++) stage[u * BLK_PER_ROUND * PITCH] = v[u];
-    }
-    __syncthreads();
-    const bool prefix_role = tid >= T / 2;  // warp-uniform
-    const int owner = tid & (T / 2 - 1);
-    float xr[PER_THREAD][W];
+        __syncthreads();
+        if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);
+        float xr[PER_THREAD][W];
 #pragma unroll
-    for (int m = 0; m < PER_THREAD; m++) {
-        const float* p = P + (owner * PER_THREAD + m) * PITCH;
+        for (int m = 0; m < PER_THREAD; m++) {
+            const float* p = P + (owner * PER_THREAD + m) * PITCH;
 #pragma unroll
-        for (int k = 0; k < W; k++) xr[m][k] = p[k];
-    }
-    __syncthreads();  // every block is in registers before P is overwritten in place
+            for (int k = 0; k < W; k++) xr[m][k] = p[k];
+        }
+        __syncthreads();  // every block is in registers before P is overwritten in place
 #pragma unroll
-    for (int m = 0; m < PER_THREAD; m++) {
-        const int b = owner * PER_THREAD + m;
-        if (prefix_role) {
-            float* p = P + b * PITCH;
-            float run = xr[m][0];
+        for (int m = 0; m < PER_THREAD; m++) {
+            const int b = owner * PER_THREAD + m;
+            if (prefix_role) {
+                float* p = P + b * PITCH;
+                float run = xr[m][0];
 #pragma unroll
-            for (int k = 1; k < W; k++) {
-                run = racc<OP>(run, xr[m][k]);
-                p[k] = run;
+                for (int k = 1; k < W; k++) {
+                    run = racc<OP>(run, xr[m][k]);
+                    p[k] = run;
+                }
+            } else {
+                float* sfx = S + b * PITCH;
+                float run = xr[m][W - 1];
+                sfx[W - 1] = run;
+#pragma unroll
+                for (int k = W - 2; k >= 0; k--) {
+                    run = racc<OP>(xr[m][k], run);
+                    sfx[k] = run;
+                }
+            }
+        }
+        __syncthreads();
+        // output e = u*T + tid: S[b][kk] (+) P[b+1][kk-1], b = u*T/W + tid/W
+        const size_t i0 = (size_t)tile * TILE;
+        float* dst = out + i0 + tid;
+        if (i0 + TILE <= nout) {
+#pragma unroll
+            for (int u = 0; u < kWinLoads; u++) {
+                if (u * T + tid < TILE) {  // only the last round is partial (TILE = SPAN - W)
+                    float r = s_lane[u * BLK_PER_ROUND * PITCH];
+                    if (has_head) r = racc<OP>(r, p_lane[u * BLK_PER_ROUND * PITCH]);
+                    __stcs(dst + u * T, rfinal_fast<OP>(init, r, ident));
+                }
             }
         } else {
-            float* sfx = S + b * PITCH;
-            float run = xr[m][W - 1];
-            sfx[W - 1] = run;
 #pragma unroll
-            for (int k = W - 2; k >= 0; k--) {
-                run = racc<OP>(xr[m][k], run);
-                sfx[k] = run;
+            for (int u = 0; u < kWinLoads; u++) {
+                if (u * T + tid < TILE && i0 + u * T + tid < nout) {
+                    float r = s_lane[u * BLK_PER_ROUND * PITCH];
+                    if (has_head) r = racc<OP>(r, p_lane[u * BLK_PER_ROUND * PITCH]);
+                    __stcs(dst + u * T, rfinal_fast<OP>(init, r, ident));
+                }
             }
         }
-    }
-    __syncthreads();
-    // output e = u*T + tid: S[b][kk] (+) P[b+1][kk-1], b = u*T/W + tid/W
-    const float* const s_lane = S + (tid >> SHIFT) * PITCH + kk;
-    const float* const p_lane = P + ((tid >> SHIFT) + 1) * PITCH + kk - 1;
-    float* dst = out + i0 + tid;
-    const bool has_head = kk != 0;
-    const bool ident = init_is_identity != 0;
-    if (i0 + TILE <= nout) {
-#pragma unroll
-        for (int u = 0; u < kWinLoads; u++) {
-            if (u * T + tid < TILE) {  // only the last round is partial (TILE = SPAN - W)
-                float v = s_lane[u * BLK_PER_ROUND * PITCH];
-                if (has_head) v = racc<OP>(v, p_lane[u * BLK_PER_ROUND * PITCH]);
-                __stcs(dst + u * T, rfinal_fast<OP>(init, v, ident));
-            }
-        }
-    } else {
-#pragma unroll
-        for (int u = 0; u < kWinLoads; u++) {
-            if (u * T + tid < TILE && i0 + u * T + tid < nout) {
-                float v = s_lane[u * BLK_PER_ROUND * PITCH];
-                if (has_head) v = racc<OP>(v, p_lane[u * BLK_PER_ROUND * PITCH]);
-                __stcs(dst + u * T, rfinal_fast<OP>(init, v, ident));
-            }
-        }
+        __syncthreads();  // P and S are free again before the next tile is parked
     }
 }
 
@@ -466,8 +476,11 @@ static bool launch_window_fixed(const float* src, float* out, uint32_t nout, flo
             return false;
         configured = true;
     }
-    const unsigned blocks = (unsigned)(((uint64_t)nout + TILE - 1) / TILE);
-    reduce_window_fixed_kernel<OP, W><<<blocks, kWinFixedThreads, smem, rt().stream>>>(src, out, nout, init, init_is_identity);
+    const unsigned n_tiles = (unsigned)(((uint64_t)nout + TILE - 1) / TILE);
+    const long per_sm = rt().window_ctas_per_sm > 0 ? rt().window_ctas_per_sm : 16;  // 4 resident, the rest queue (tail balance)
+    unsigned blocks = (unsigned)(kNumSMs * per_sm);
+    if (blocks > n_tiles) blocks = n_tiles;
+    reduce_window_fixed_kernel<OP, W><<<blocks, kWinFixedThreads, smem, rt().stream>>>(src, out, nout, n_tiles, init, init_is_identity);
     note_launch("reduce_window");
     return check_launch("reduce_window");
 }

@@ -342,6 +342,7 @@ int al_set_tuning(const char* key, long value) {
     else if (k == "force_general") g_rt.force_general = value;
     else if (k == "reduce_splits") g_rt.reduce_splits = value;
     else if (k == "disable_window") g_rt.disable_window = value;
+    else if (k == "window_ctas_per_sm") g_rt.window_ctas_per_sm = value;
     else if (k == "tile64") g_rt.tile64 = value;
     else if (k == "outer_tile") g_rt.outer_tile = value;
     else {
