@@ -82,6 +82,8 @@ def _load():
     sig("array_arange", ArrayP, F32, F32, F32)
     sig("array_linspace", ArrayP, F32, F32, F32)
     sig("array_to_host", C.c_int, ArrayP, C.c_void_p)
+    sig("array_fill_async", ArrayP, C.c_void_p, SizeP, C.c_size_t)
+    sig("array_to_host_async", C.c_int, ArrayP, C.c_void_p)
     sig("array_read_base", C.c_int, ArrayP, C.c_size_t, C.c_size_t, C.c_void_p)
     sig("array_write_base", C.c_int, ArrayP, C.c_size_t, C.c_size_t, C.c_void_p)
     sig("array_get_elem", F32, ArrayP, SizeP)

@@ -316,22 +316,30 @@ def linspace(start: int, end: int, n: int) -> NDArray:
 # -------------------------------------------------------------------------------------------------
 
 
-def from_numpy(array) -> NDArray:
-    """Upload a float32 numpy array (any strides; 0-d becomes shape (1,))."""
+def from_numpy(array, blocking=True) -> NDArray:
+    """Upload a float32 numpy array (any strides; 0-d becomes shape (1,)).
+
+    `blocking=False` (extension): `array` must be C-contiguous PINNED memory (`host_buffer`) that is
+    left untouched until `synchronize()`; the copy then runs on the library's H2D stream."""
     import numpy as np
 
     assert isinstance(array, np.ndarray), f"expected numpy array, got {type(array)=}"
     assert array.dtype == np.float32, f"expected float32 dtype, got {array.dtype=}"
     host = np.ascontiguousarray(array)
     shape = host.shape if host.ndim else (1,)
+    if not blocking:
+        assert host is array or host.ctypes.data == array.ctypes.data, "blocking=False needs a C-contiguous array"
+        return _new(lib.array_fill_async(C.c_void_p(host.ctypes.data), size_array(shape), len(shape)))
     return _new(lib.array_fill(C.c_void_p(host.ctypes.data), size_array(shape), len(shape)))
 
 
-def to_numpy(array: NDArray, out=None):
+def to_numpy(array: NDArray, out=None, blocking=True):
     """Device -> host COPY of the logical view (honours strides and the view offset).
 
     `out` (optional, extension): a C-contiguous float32 array of the same shape to copy into,
-    e.g. one backed by pinned memory from `host_buffer`."""
+    e.g. one backed by pinned memory from `host_buffer`. With `blocking=False` (needs a pinned
+    `out`) the copy is only enqueued on the library's D2H stream; `out` is valid after
+    `synchronize()`."""
     import numpy as np
 
     assert isinstance(array, NDArray)
@@ -340,6 +348,9 @@ def to_numpy(array: NDArray, out=None):
     else:
         assert isinstance(out, np.ndarray) and out.dtype == np.float32 and out.flags.c_contiguous
         assert out.shape == array.shape
+    if not blocking:
+        check_rc(lib.array_to_host_async(array.buffer, C.c_void_p(out.ctypes.data)))
+        return out
     check_rc(lib.array_to_host(array.buffer, C.c_void_p(out.ctypes.data)))
     return out
 

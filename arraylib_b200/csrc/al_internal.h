@@ -23,7 +23,10 @@ constexpr int kNumSMs = 148;  // B200
 // ---- per-process runtime -------------------------------------------------------------------
 struct Runtime {
     int device = -1;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // every kernel and every blocking copy
+    cudaStream_t h2d_stream = nullptr;  // asynchronous uploads (array_fill_async)
+    cudaStream_t d2h_stream = nullptr;  // asynchronous downloads (array_to_host_async)
+    cudaEvent_t ev_copy = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     uint64_t launches = 0;
     const char* last_kernel = "";
@@ -37,6 +40,7 @@ struct Runtime {
     long disable_window = 0;
     long window_ctas_per_sm = 0;  // 0 = default (16 CTAs per SM, 4 of them resident)
     long tile64 = 1;           // 0: use the 32x32 scalar transpose tile even when the float4 one applies
+    long tile_tq = 64;         // q extent of the 128-bit transpose tile: 32, 64 or 128 (p extent = 4096 / tq)
     long outer_tile = 1;       // 0: do not use the register-tiled outer-broadcast kernel
 };
 Runtime& rt();

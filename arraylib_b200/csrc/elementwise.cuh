@@ -332,12 +332,14 @@ __global__ void __launch_bounds__(kTile * kTileRows) ew_tile_kernel(const TileAr
 // Shared memory is addressed in float4 units, 16 units per tile row, with unit' = unit ^ ((row>>2)&7):
 // both the store phase (8 lanes of a quarter-warp hit rows 4 apart) and the load phase (8 lanes hit
 // consecutive units of one row) then cover all 32 banks exactly once.
-constexpr int kT64 = 64;
-
-template <typename F>
+// The tile is TQ (along q) x TP (along p) with TQ*TP = 4096, TQ in {32, 64, 128}: a wider TP makes the
+// p-major READ runs longer (TP*4 bytes per row), a wider TQ the q-major WRITE runs.
+template <typename F, int TQ>
 __global__ void __launch_bounds__(256) ew_tile64_kernel(const TileArgs<F::NIN> a, const F f) {
     constexpr int NIN = F::NIN;
-    __shared__ float4 tile[NIN][kT64 * 16];
+    constexpr int TP = 4096 / TQ, UQ = TQ / 4, P4 = TP / 4, ROWS_PER_PASS = 256 / UQ;
+    static_assert(UQ >= 8 && P4 >= 8, "swizzle needs at least 8 float4 units per row and 8 p-groups");
+    __shared__ float4 tile[NIN][TP * UQ];
     // (A grouped 8x8 CTA order was measured and gave no gain over this q-fastest order.)
     uint32_t t = blockIdx.x;
     uint32_t r = fdiv(t, a.div_tq);
@@ -360,8 +362,8 @@ __global__ void __launch_bounds__(256) ew_tile64_kernel(const TileArgs<F::NIN> a
 #pragma unroll
         for (int i = 0; i < NIN; i++) ibase[i] += (long long)idx * a.bstride[i][d];
     }
-    const uint32_t q0 = tq * kT64, p0 = tp * kT64;
-    const uint32_t lo = threadIdx.x & 15, hi = threadIdx.x >> 4;
+    const uint32_t q0 = tq * TQ, p0 = tp * TP;
+    const uint32_t lo = threadIdx.x % P4, hi = threadIdx.x / P4;
     // stage: lo indexes float4 along p, hi indexes 4-row groups along q
 #pragma unroll
     for (int i = 0; i < NIN; i++) {
@@ -376,21 +378,22 @@ __global__ void __launch_bounds__(256) ew_tile64_kernel(const TileArgs<F::NIN> a
                            : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             const uint32_t sw = hi ^ (lo & 7);
-            tile[i][(4 * lo + 0) * 16 + sw] = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
-            tile[i][(4 * lo + 1) * 16 + sw] = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
-            tile[i][(4 * lo + 2) * 16 + sw] = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
-            tile[i][(4 * lo + 3) * 16 + sw] = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
+            tile[i][(4 * lo + 0) * UQ + sw] = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
+            tile[i][(4 * lo + 1) * UQ + sw] = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
+            tile[i][(4 * lo + 2) * UQ + sw] = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
+            tile[i][(4 * lo + 3) * UQ + sw] = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
         }
     }
     // operands that are already q-major are fetched now, so their latency overlaps the staging above
-    const uint32_t q = q0 + 4 * lo;
+    const uint32_t eu = threadIdx.x % UQ, er = threadIdx.x / UQ;  // emit role: float4 unit along q, row along p
+    const uint32_t q = q0 + 4 * eu;
     float4 direct[NIN][4];
 #pragma unroll
     for (int i = 0; i < NIN; i++) {
         if (!(a.via_smem >> i & 1)) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const uint32_t p = p0 + hi + 16 * j;
+                const uint32_t p = p0 + er + ROWS_PER_PASS * j;
                 if (q < a.ext_q && p < a.ext_p) {
                     const float* src = a.in[i] + ibase[i] + (long long)q * a.sq[i] + (long long)p * a.sp[i];
                     if (a.sq[i] == 0) {
@@ -404,16 +407,16 @@ __global__ void __launch_bounds__(256) ew_tile64_kernel(const TileArgs<F::NIN> a
         }
     }
     __syncthreads();
-    // emit: lo indexes float4 along q, rows (p) = hi + 16*j
+    // emit: eu indexes float4 along q, rows (p) = er + ROWS_PER_PASS*j
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const uint32_t row = hi + 16 * j;
+        const uint32_t row = er + ROWS_PER_PASS * j;
         const uint32_t p = p0 + row;
         if (q < a.ext_q && p < a.ext_p) {
             float4 x[NIN];
 #pragma unroll
             for (int i = 0; i < NIN; i++) {
-                if (a.via_smem >> i & 1) x[i] = tile[i][row * 16 + (lo ^ ((row >> 2) & 7))];
+                if (a.via_smem >> i & 1) x[i] = tile[i][row * UQ + (eu ^ ((row >> 2) & 7))];
                 else x[i] = direct[i][j];
             }
             float4 y;
@@ -644,13 +647,17 @@ static bool launch_tile(const F& f, const Folded& fo, const float* const* in, fl
             if ((smem || a.sq[i] == 1) && a.bstride[i][d] % 4 != 0) wide = false;
     }
     if (wide) {
-        a.tiles_q = (a.ext_q + kT64 - 1) / kT64;
-        a.tiles_p = (a.ext_p + kT64 - 1) / kT64;
+        const int tq = rt().tile_tq == 32 || rt().tile_tq == 128 ? (int)rt().tile_tq : 64;
+        const int tp = 4096 / tq;
+        a.tiles_q = (a.ext_q + tq - 1) / tq;
+        a.tiles_p = (a.ext_p + tp - 1) / tp;
         a.div_tq = make_fastdiv(a.tiles_q);
         a.div_tp = make_fastdiv(a.tiles_p);
         uint64_t blocks64 = (uint64_t)a.tiles_q * a.tiles_p * nb;
         if (blocks64 >= (1ull << 31)) return false;
-        ew_tile64_kernel<F><<<(unsigned)blocks64, 256, 0, rt().stream>>>(a, f);
+        if (tq == 32) ew_tile64_kernel<F, 32><<<(unsigned)blocks64, 256, 0, rt().stream>>>(a, f);
+        else if (tq == 128) ew_tile64_kernel<F, 128><<<(unsigned)blocks64, 256, 0, rt().stream>>>(a, f);
+        else ew_tile64_kernel<F, 64><<<(unsigned)blocks64, 256, 0, rt().stream>>>(a, f);
         note_launch("ew_tile64_transpose");
         return check_launch("ew_tile64");
     }

@@ -253,6 +253,9 @@ int al_init(int device) {
     if (device >= count) device = device % count;
     if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return -1;
     if (!cuda_ok(cudaStreamCreateWithFlags(&g_rt.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return -1;
+    if (!cuda_ok(cudaStreamCreateWithFlags(&g_rt.h2d_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return -1;
+    if (!cuda_ok(cudaStreamCreateWithFlags(&g_rt.d2h_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return -1;
+    if (!cuda_ok(cudaEventCreateWithFlags(&g_rt.ev_copy, cudaEventDisableTiming), "cudaEventCreate")) return -1;
     if (!cuda_ok(cudaEventCreate(&g_rt.ev_start), "cudaEventCreate")) return -1;
     if (!cuda_ok(cudaEventCreate(&g_rt.ev_stop), "cudaEventCreate")) return -1;
     g_rt.device = device;
@@ -262,10 +265,24 @@ int al_init(int device) {
 
 int al_device(void) { return g_rt.device; }
 
+// Blocks that an in-flight asynchronous download still reads: they hold one extra reference until
+// the copy stream has been drained, so the allocator cannot hand them to a new owner early.
+static std::vector<NDArray*> g_pending_downloads;
+
+static void drain_pending_downloads() {
+    std::vector<NDArray*> done;
+    done.swap(g_pending_downloads);
+    for (NDArray* a : done) array_free(a);
+}
+
 int al_sync(void) {
     AL_ENTER;
     if (g_rt.device < 0) return 0;
-    return cuda_ok(cudaStreamSynchronize(g_rt.stream), "cudaStreamSynchronize") ? 0 : -1;
+    bool ok = cuda_ok(cudaStreamSynchronize(g_rt.h2d_stream), "cudaStreamSynchronize(h2d)") &&
+              cuda_ok(cudaStreamSynchronize(g_rt.stream), "cudaStreamSynchronize") &&
+              cuda_ok(cudaStreamSynchronize(g_rt.d2h_stream), "cudaStreamSynchronize(d2h)");
+    drain_pending_downloads();
+    return ok ? 0 : -1;
 }
 
 void* al_stream(void) { return (void*)g_rt.stream; }
@@ -344,6 +361,7 @@ int al_set_tuning(const char* key, long value) {
     else if (k == "disable_window") g_rt.disable_window = value;
     else if (k == "window_ctas_per_sm") g_rt.window_ctas_per_sm = value;
     else if (k == "tile64") g_rt.tile64 = value;
+    else if (k == "tile_tq") g_rt.tile_tq = value;
     else if (k == "outer_tile") g_rt.outer_tile = value;
     else {
         set_error("KeyError: unknown tuning key '%s'", k.c_str());
@@ -412,6 +430,47 @@ NDArray* array_fill(f32* elems, const size_t* shape, size_t ndim) {
         return nullptr;
     }
     return a;
+}
+
+// Asynchronous upload (extension): the copy runs on a dedicated H2D stream and the compute stream
+// waits for it, so the call returns at once and overlaps with downloads and kernels. `elems` must
+// be pinned (al_host_alloc) and stay untouched until al_sync().
+NDArray* array_fill_async(f32* elems, const size_t* shape, size_t ndim) {
+    AL_ENTER;
+    AL_REQUIRE(elems, "TypeError: array_fill_async got a NULL host buffer");
+    NDArray* a = new_array(shape, ndim);
+    if (!a) return nullptr;
+    // the block may have just been released by work still queued on the compute stream
+    bool ok = cuda_ok(cudaEventRecord(g_rt.ev_copy, g_rt.stream), "cudaEventRecord") &&
+              cuda_ok(cudaStreamWaitEvent(g_rt.h2d_stream, g_rt.ev_copy, 0), "cudaStreamWaitEvent") &&
+              cuda_ok(cudaMemcpyAsync(a->ptr, elems, a->data->size * sizeof(float), cudaMemcpyHostToDevice,
+                                      g_rt.h2d_stream), "cudaMemcpyAsync(H2D)") &&
+              cuda_ok(cudaEventRecord(g_rt.ev_copy, g_rt.h2d_stream), "cudaEventRecord") &&
+              cuda_ok(cudaStreamWaitEvent(g_rt.stream, g_rt.ev_copy, 0), "cudaStreamWaitEvent");
+    if (!ok) {
+        std::string keep = g_err;
+        array_free(a);
+        g_err = keep;
+        return nullptr;
+    }
+    return a;
+}
+
+// Asynchronous download (extension): ordered after everything enqueued so far, executed on a
+// dedicated D2H stream. `dst` must be pinned and is valid after al_sync().
+int array_to_host_async(const NDArray* src, f32* dst) {
+    AL_ENTER;
+    if (!valid(src, "array_to_host_async")) return -1;
+    if (!dst) return set_error("TypeError: array_to_host_async got a NULL destination"), -1;
+    size_t n = count_of(src->lay->shape, src->lay->ndim);
+    NDArray* hold = is_contiguous(src) ? array_shallow_copy(src) : array_deep_copy(src);
+    if (!hold) return -1;
+    bool ok = cuda_ok(cudaEventRecord(g_rt.ev_copy, g_rt.stream), "cudaEventRecord") &&
+              cuda_ok(cudaStreamWaitEvent(g_rt.d2h_stream, g_rt.ev_copy, 0), "cudaStreamWaitEvent") &&
+              cuda_ok(cudaMemcpyAsync(dst, hold->ptr, n * sizeof(float), cudaMemcpyDeviceToHost, g_rt.d2h_stream),
+                      "cudaMemcpyAsync(D2H)");
+    g_pending_downloads.push_back(hold);  // released by al_sync()
+    return ok ? 0 : -1;
 }
 
 // arraylib.c:298-308. While every value and every partial sum stays <= 2^24 the reference's

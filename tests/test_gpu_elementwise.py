@@ -148,6 +148,13 @@ def test_tile64_equals_tile32(al, rng, shape, perm):
     for wv, nv, ref_ in zip(wide, narrow, [np.transpose(x, perm) - y, np.transpose(x, perm)]):
         assert_bit_equal(wv, nv, "tile64 vs tile32")
         assert_bit_equal(wv, ref_, "tile64 vs numpy")
+    for tq in (32, 128):  # the other tile aspect ratios
+        lib.al_set_tuning(b"tile_tq", tq)
+        try:
+            assert_bit_equal(al.to_numpy(X.transpose(perm) - Y), np.transpose(x, perm) - y, f"tile_tq={tq}")
+            assert_bit_equal(al.to_numpy(al.copy(X.transpose(perm), deep=True)), np.transpose(x, perm), f"copy tile_tq={tq}")
+        finally:
+            lib.al_set_tuning(b"tile_tq", 64)
 
 
 def test_outer_broadcast_plan_is_used_and_exact(al, orc, rng):

@@ -164,3 +164,24 @@ def test_matmul_dot(al, orc, rng):
     u, v = np.arange(1, 50, dtype=np.float32), np.arange(2, 51, dtype=np.float32)
     d = al.dot(al.from_numpy(u), al.from_numpy(v))
     assert d.shape == (1,) and float(d) == float(np.dot(u.astype(np.float64), v.astype(np.float64)))
+
+
+def test_async_host_transfers(al, rng):
+    """Pinned staging + the non-blocking upload / download streams give the same bits."""
+    hin = al.host_buffer((3, 1000, 70))
+    hin[...] = rng.standard_normal((3, 1000, 70)).astype(np.float32)
+    hout = al.host_buffer((3, 1000, 70))
+    outs = []
+    for k in range(4):  # several transfers in flight at once, blocks recycled underneath
+        X = al.from_numpy(hin, blocking=False)
+        Y = X * float(k + 1) + 0.5
+        o = al.host_buffer((3, 1000, 70))
+        al.to_numpy(Y, out=o, blocking=False)
+        del X, Y
+        outs.append(o)
+    T = al.from_numpy(hin, blocking=False).transpose((2, 0, 1))
+    al.to_numpy(T, out=hout.reshape(70, 3, 1000), blocking=False)  # non-contiguous source: gathered first
+    al.synchronize()
+    for k, o in enumerate(outs):
+        assert_bit_equal(o, hin * np.float32(k + 1) + np.float32(0.5), f"async {k}")
+    assert_bit_equal(hout.reshape(70, 3, 1000), np.transpose(hin, (2, 0, 1)), "async transposed")

@@ -77,8 +77,11 @@ def bench_bcast():
 def bench_transpose():
     m = 16384
     X, Y = rnd((m, m), 1), rnd((m, m), 2)
-    timed(lambda: X.transpose((1, 0)) + Y, 12 * m * m, "X.T + Y 16384^2")
-    timed(lambda: X.transpose((1, 0)).reshape((m * m,)), 8 * m * m, "X.T.reshape (strided copy) 16384^2")
+    for tq in (32, 64, 128):
+        tune(tile_tq=tq)
+        timed(lambda: X.transpose((1, 0)) + Y, 12 * m * m, f"X.T + Y 16384^2 tile_tq={tq}")
+        timed(lambda: X.transpose((1, 0)).reshape((m * m,)), 8 * m * m, f"X.T.reshape (strided copy) 16384^2 tile_tq={tq}")
+    tune(tile_tq=64)
     tune(force_general=1)
     timed(lambda: X.transpose((1, 0)) + Y, 12 * m * m, "X.T + Y 16384^2 (scalar gather fallback)", reps=3)
     tune(force_general=0)
@@ -107,6 +110,10 @@ def bench_reduce():
     for dims in ((1, 2), (3,), (0,), (0, 1, 2, 3), (0, 1, 2), (2, 3), (1,)):
         timed(lambda: X.reduce_sum(dims=dims), 4 * n, f"reduce_sum [64,512,512,64] dims={dims}")
     timed(lambda: X.reduce_max(dims=(1, 2)), 4 * n, "reduce_max dims=(1,2)")
+    for splits in (9, 18, 37, 74, 148, 296):
+        tune(reduce_splits=splits)
+        timed(lambda: X.reduce_sum(dims=(1, 2)), 4 * n, f"reduce_sum dims=(1,2) splits={splits}")
+    tune(reduce_splits=0)
 
 
 if __name__ == "__main__":
