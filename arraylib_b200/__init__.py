@@ -6,3 +6,4 @@ names as the reference's `arraylib` package; buffers live in GPU HBM behind liba
 from arraylib_b200.core import *  # noqa: F401,F403
 from arraylib_b200.core import NDArray, Layout, synchronize, full, mod  # noqa: F401
 from arraylib_b200 import core, ufuncs  # noqa: F401
+from arraylib_b200.lazy import Expr, fused, lazy  # noqa: F401,E402

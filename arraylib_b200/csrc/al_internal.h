@@ -41,6 +41,7 @@ struct Runtime {
     long window_ctas_per_sm = 0;  // 0 = default (16 CTAs per SM, 4 of them resident)
     long tile64 = 1;           // 0: use the 32x32 scalar transpose tile even when the float4 one applies
     long tile_tq = 64;         // q extent of the 128-bit transpose tile: 32, 64 or 128 (p extent = 4096 / tq)
+    long chain_block = 2;      // fused chains: 0 one vector per thread, 1 generic 4-row blocks, 2 also the specialised 8-row kernel
     long outer_tile = 1;       // 0: do not use the register-tiled outer-broadcast kernel
 };
 Runtime& rt();
@@ -86,7 +87,7 @@ struct Folded {
     int ndim = 0;
     uint64_t extent[kMaxDims];
     int64_t out_stride[kMaxDims];
-    int64_t in_stride[3][kMaxDims];
+    int64_t in_stride[4][kMaxDims];  // up to 4 operands (the fused chain kernel takes 4)
 };
 // Collapse an iteration space of `ndim` logical axes over `nin` strided operands and one
 // strided output: extent-1 axes are dropped and neighbours that are mutually contiguous in every

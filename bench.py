@@ -291,6 +291,33 @@ def run_gpu(args):
                 "frac": round(dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, 3), "traffic": traffic,
                 "algorithmic_bytes_per_launch": int(dom_bytes), "avg_launch_ms": round(dom_ms, 4), "launches_per_step": len(dom)}
 
+    # ---- fused chain (reported separately; NOT part of `value`, which is the eager suite) ----
+    fused = None
+    try:
+        def chain():
+            return (al.lazy(dev["A"]) + dev["B"] + dev["c"]).eval()
+        for _ in range(2):
+            r = chain()
+            del r
+        ts = []
+        for _ in range(5):
+            lib.al_event_record(60000)
+            r = chain()
+            lib.al_event_record(60001)
+            e = C.c_float()
+            assert lib.al_event_elapsed(60000, 60001, C.byref(e)) == 0
+            ts.append(float(e.value))
+            del r
+        fms = statistics.median(ts)
+        eager_bytes = nbytes["c3_bcast_add"] + nbytes["c3_bcast_add_vec"]
+        fused_bytes = 4 * c3[0] * c3[1] * c3[2] + 4 * (c3[0] * c3[2] + c3[1] * c3[2] + c3[2])
+        fused = {"op": "c3 chain A+B+c as ONE kernel (al.lazy(...).eval())", "ms": round(fms, 4), "kernel": lib.al_last_kernel().decode(),
+                 "eager_ms": round(per_op["c3_bcast_add"]["ms"] + per_op["c3_bcast_add_vec"]["ms"], 4),
+                 "gbs_vs_eager_algorithmic_bytes": round(eager_bytes / (fms * 1e-3) / 1e9, 1),
+                 "gbs_vs_fused_algorithmic_bytes": round(fused_bytes / (fms * 1e-3) / 1e9, 1)}
+    except Exception as exc:
+        fused = {"error": repr(exc)}
+
     # ---- e2e: host buffers in, host buffers out, through the public API ----
     e2e = None
     if not args.no_e2e:
@@ -362,7 +389,7 @@ def run_gpu(args):
                    "sharding": "leading axis, one shard of the named shape per GPU", "l2_policy": "inputs larger than L2 (>=1 GiB per operand); no flush",
                    "algorithmic_bytes_per_step_per_gpu": int(step_bytes)},
         "pct_of_8TBs_per_gpu": round(100 * value / world / NOMINAL_GBS, 1),
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "ops": per_op, "e2e": e2e, "cpu_baseline": cpu_baseline,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "ops": per_op, "fused_chain": fused, "e2e": e2e, "cpu_baseline": cpu_baseline,
     }
     return line
 

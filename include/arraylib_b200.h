@@ -157,6 +157,18 @@ NDArray* array_array_le(const NDArray* lhs, const NDArray* rhs);
 NDArray* array_array_matmul(const NDArray* lhs, const NDArray* rhs); /* arraylib.c:522-564 (compat) */
 NDArray* array_array_dot(const NDArray* lhs, const NDArray* rhs);    /* arraylib.c:671-688 (compat) */
 
+/* ---- fused elementwise chain (extension; replaces several eager array_array_op / array_scalar_op
+ *      passes, arraylib.c:491-501,569-589, by one pass; results are bit-identical to the eager ones) */
+typedef struct {
+    int kind;     /* 0: acc = binop(acc, next array)  1: acc = binop(next array, acc)
+                     2: acc = binop(acc, scalar)      3: acc = binop(scalar, acc)   4: acc = ufunc(acc) */
+    int op;       /* al_binop (kinds 0-3) or al_ufunc (kind 4) */
+    f32 scalar;   /* kinds 2 and 3 */
+} al_chain_step;
+/* acc starts as inputs[0]; array-consuming steps take inputs[1], inputs[2], ... in order.
+ * At most 4 arrays and 8 steps; all arrays broadcast against each other (NumPy rule). */
+NDArray* array_chain_eval(const NDArray* const* inputs, size_t n_inputs, const al_chain_step* steps, size_t n_steps);
+
 /* ---- unary ufunc table (arraylib.c:638-665) ----------------------------------------------- */
 typedef f32 (*binop)(f32, f32);
 typedef f32 (*uniop)(f32);

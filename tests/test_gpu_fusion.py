@@ -1,0 +1,81 @@
+"""Fused elementwise chains must be bit-identical to the eager (reference-order) evaluation."""
+import math
+
+import numpy as np
+import pytest
+
+from tests.conftest import assert_bit_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def test_readme_broadcast_chain_fused(al):
+    eager = al.ones([3, 6]) + al.ones([6]) + al.ones([4, 3, 1]) + 1.0
+    fused = (al.lazy(al.ones([3, 6])) + al.ones([6]) + al.ones([4, 3, 1]) + 1.0).eval()
+    assert fused.shape == (4, 3, 6) and fused.stride == eager.stride
+    assert_bit_equal(al.to_numpy(fused), al.to_numpy(eager))
+
+
+@pytest.mark.parametrize("shapes", [((64, 1, 256), (1, 48, 256), (256,)), ((7, 5), (5,), (7, 1)), ((1000,), (1000,), (1,)),
+                                    ((3, 1, 9), (4, 1), (9,)), ((33, 130), (130,), (33, 130))])
+def test_three_operand_chains(al, orc, rng, shapes):
+    from arraylib_b200._lib import lib
+    xs = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    X = [al.from_numpy(x) for x in xs]
+    got = (al.lazy(X[0]) + X[1] + X[2] + 1.0).eval()
+    assert lib.al_last_kernel().startswith(b"ew_chain")
+    want = orc.binary("sum", orc.binary("sum", orc.binary("sum", xs[0], xs[1]), xs[2]), 1.0)
+    assert_bit_equal(al.to_numpy(got), want, "a+b+c+1")
+    got = al.fused(lambda a, b, c: (2.0 - a * b) / c, *X)
+    want = orc.binary("div", al.to_numpy(2.0 - X[0] * X[1]), xs[2])
+    assert_bit_equal(al.to_numpy(got), want, "(2-a*b)/c")
+    assert_bit_equal(al.to_numpy(got), al.to_numpy((2.0 - X[0] * X[1]) / X[2]), "vs eager")
+
+
+def test_unary_steps_reversed_operands_and_long_chains(al, orc, rng):
+    a = np.abs(rng.standard_normal((50, 40))).astype(np.float32) + np.float32(0.5)
+    b = rng.standard_normal((40,)).astype(np.float32)
+    A, B = al.from_numpy(a), al.from_numpy(b)
+    got = al.fused(lambda x, y: (x.sqrt() * y).abs().apply(math.log) - 3.0, A, B)
+    want = al.log(al.abs(al.sqrt(A) * B)) - 3.0
+    assert_bit_equal(al.to_numpy(got), al.to_numpy(want), "sqrt/abs/log chain")
+    # B - lazy(A): array on the left of the running value
+    assert_bit_equal(al.to_numpy((B - al.lazy(A)).eval()) if False else al.to_numpy(al.lazy(A).__rsub__(B).eval()), al.to_numpy(B - A), "rsub")
+    # longer than 8 steps / more than 4 arrays: flushed through temporaries, still exact
+    e, ref = al.lazy(A), A
+    for k in range(11):
+        e, ref = e + B, ref + B
+        e, ref = e * float(k + 1), ref * float(k + 1)
+    assert_bit_equal(al.to_numpy(e.eval()), al.to_numpy(ref), "long chain")
+    # transposed operand inside a chain (scalar path) and comparison ops
+    T = al.from_numpy(rng.standard_normal((40, 50)).astype(np.float32)).transpose((1, 0))
+    assert_bit_equal(al.to_numpy((al.lazy(A) + T > 1.0).eval()), al.to_numpy(al.gt(A + T, 1.0)), "transposed + cmp")
+
+
+def test_chain_errors(al):
+    with pytest.raises(ValueError):
+        (al.lazy(al.ones((2, 3))) + al.ones((4,))).eval()
+    with pytest.raises(NotImplementedError):
+        al.lazy(al.ones((2, 3))).apply(lambda v: v * v + 1.0)
+
+
+@pytest.mark.parametrize("shapes", [((37, 1, 64), (1, 29, 64), (64,), (37, 29, 64)), ((19, 24), (24,), (19, 1), (1, 24)),
+                                    ((5, 9, 3, 8), (9, 1, 8), (3, 8), (5, 1, 1, 8)), ((100, 12), (100, 12), (100, 12), (100, 12))])
+def test_four_operand_chains_all_kernels_agree(al, orc, rng, shapes):
+    """The specialised 8-row kernel, the generic 4-row kernel and the unblocked kernel are the same
+    computation; all must equal the eager result bit for bit."""
+    from arraylib_b200._lib import lib
+    xs = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    X = [al.from_numpy(x) for x in xs]
+    eager = al.to_numpy(al.max((X[0] - X[1]) * X[2], X[3]) / 3.0)
+    seen = set()
+    for mode in (2, 1, 0):
+        lib.al_set_tuning(b"chain_block", mode)
+        try:
+            got = al.fused(lambda a, b, c, d: ((a - b) * c).maximum(d) / 3.0, *X)
+            seen.add(lib.al_last_kernel())
+        finally:
+            lib.al_set_tuning(b"chain_block", 2)
+        assert_bit_equal(al.to_numpy(got), eager, f"chain_block={mode}")
+    if len(set(shapes)) > 1:  # identical contiguous operands fold to a 1-D stream: nothing to block
+        assert len(seen) >= 2, seen
