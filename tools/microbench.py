@@ -116,6 +116,18 @@ def bench_reduce():
     tune(reduce_splits=0)
 
 
+def bench_ops():
+    n = 1 << 28
+    a, b = rnd((n,), 1), rnd((n,), 2)
+    pos = al.abs(a) + 0.5
+    for name in ("add", "sub", "mul", "div", "mod", "pow", "max", "min", "eq", "ne", "gt", "ge", "lt", "le"):
+        x = pos if name == "pow" else a
+        timed(lambda: getattr(al, name)(x, b), 12 * n, f"binary {name} 2^28", reps=3, warm=1)
+    for name in ("neg", "abs", "sqrt", "exp", "log", "sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh",
+                 "asinh", "acosh", "atanh", "ceil", "floor"):
+        timed(lambda: getattr(al, name)(pos), 8 * n, f"unary {name} 2^28", reps=3, warm=1)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["fill", "ew", "bcast", "transpose", "window", "reduce"]
     for w in which:
