@@ -486,10 +486,24 @@ floor = generate_unary_op("floor")
 
 
 def apply(fn, array) -> NDArray:
-    """Elementwise map. `fn` must resolve to a named device ufunc (see ufuncs.resolve_unary)."""
+    """Elementwise map on the device. `fn` is resolved, in this order, to
+      1. a named device ufunc by identity / name (math.sqrt, np.log, abs, ...);
+      2. a traced chain: arithmetic lambdas such as `lambda x: 2 * x * x + 1` or `lambda x: np.exp(-x)`
+         are recorded on a lazy proxy and run as one FP64-mode kernel (double arithmetic, one final
+         rounding: the arithmetic of the reference's per-element Python callback);
+      3. a named device ufunc by probe fingerprint (e.g. `lambda x: math.sqrt(x)`).
+    Anything else raises NotImplementedError -- there is no CPU fallback."""
     assert callable(fn) or isinstance(fn, str)
     assert isinstance(array, NDArray)
-    return _new(lib.array_op_named(_uf.resolve_unary(fn), array.buffer))
+    code = _uf.resolve_by_name(fn)
+    if code is None and not isinstance(fn, str):
+        from .lazy import trace_unary  # (the package also exports a FUNCTION named `lazy`)
+        traced = trace_unary(fn, array)
+        if traced is not None:
+            return traced
+    if code is None:
+        code = _uf.resolve_unary(fn)
+    return _new(lib.array_op_named(code, array.buffer))
 
 
 # -------------------------------------------------------------------------------------------------

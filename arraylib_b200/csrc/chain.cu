@@ -27,6 +27,7 @@ struct ChainArgs {
     unsigned char kind[kChainMaxSteps];
     unsigned char op[kChainMaxSteps];
     float scalar[kChainMaxSteps];
+    double dscalar[kChainMaxSteps];  // the same constants at full precision (FP64 mode)
 };
 
 // One chain step over N lanes. The op is decoded ONCE (the switch is outside the lane loops), so the
@@ -298,11 +299,108 @@ static void launch_blocked_inv(const ChainArgs<NIN>& ca, unsigned blocks, int in
     }
 }
 
+// ---- FP64 mode: the chain runs in double precision and rounds to f32 ONCE at the end -------------------
+// This is the arithmetic of the reference's `apply(fn)`: cffi hands the Python callback a C float
+// widened to a Python float (a double), the lambda computes in double, and the returned double is
+// narrowed to f32 (/root/reference/arraylib/core.py:455-460, arraylib.c:638-645). A traced lambda
+// therefore matches the reference bit for bit for + - * / comparisons, neg, abs, sqrt, ceil, floor (all
+// correctly rounded in IEEE double) and to the usual libm tolerance for the transcendentals.
+__device__ __forceinline__ double dbin(int op, double x, double y) {
+    switch (op) {
+        case AL_SUM: return __dadd_rn(x, y);
+        case AL_SUB: return __dsub_rn(x, y);
+        case AL_MUL: return __dmul_rn(x, y);
+        case AL_DIV: return __ddiv_rn(x, y);
+        case AL_MOD: return fmod(x, y);
+        case AL_POW: return pow(x, y);
+        case AL_MAX: return (x >= y || y != y) ? x : y;
+        case AL_MIN: return (x <= y || y != y) ? x : y;
+        case AL_EQ: return x == y ? 1.0 : 0.0;
+        case AL_NE: return x != y ? 1.0 : 0.0;
+        case AL_GT: return x > y ? 1.0 : 0.0;
+        case AL_GE: return x >= y ? 1.0 : 0.0;
+        case AL_LT: return x < y ? 1.0 : 0.0;
+        default: return x <= y ? 1.0 : 0.0;
+    }
+}
+__device__ __forceinline__ double dun(int op, double x) {
+    switch (op) {
+        case AL_NEG: return -x;
+        case AL_ABS: return fabs(x);
+        case AL_SQRT: return __dsqrt_rn(x);
+        case AL_EXP: return exp(x);
+        case AL_LOG: return log(x);
+        case AL_SIN: return sin(x);
+        case AL_COS: return cos(x);
+        case AL_TAN: return tan(x);
+        case AL_ASIN: return asin(x);
+        case AL_ACOS: return acos(x);
+        case AL_ATAN: return atan(x);
+        case AL_SINH: return sinh(x);
+        case AL_COSH: return cosh(x);
+        case AL_TANH: return tanh(x);
+        case AL_ASINH: return asinh(x);
+        case AL_ACOSH: return acosh(x);
+        case AL_ATANH: return atanh(x);
+        case AL_CEIL: return ceil(x);
+        default: return floor(x);
+    }
+}
+
+template <int NIN>
+__global__ void __launch_bounds__(kEwThreads) ew_chain_f64_kernel(const ChainArgs<NIN> ca) {
+    const NdArgs<NIN>& a = ca.nd;
+    const uint32_t item = blockIdx.x * (uint32_t)kEwThreads + threadIdx.x;
+    if (item >= a.n_items) return;
+    long long off[NIN];
+#pragma unroll
+    for (int i = 0; i < NIN; i++) off[i] = 0;
+    uint32_t rem = item;
+#pragma unroll
+    for (int d = 0; d < kMaxDims; d++) {
+        uint32_t idx;
+        const bool last = (d == a.ndim - 1);
+        if (last) {
+            idx = rem;
+        } else {
+            const uint32_t q = fdiv(rem, a.div[d]);
+            idx = rem - q * a.extent[d];
+            rem = q;
+        }
+#pragma unroll
+        for (int i = 0; i < NIN; i++) off[i] += (long long)idx * a.stride[i][d];
+        if (last) break;
+    }
+    double v[NIN];
+#pragma unroll
+    for (int i = 0; i < NIN; i++) v[i] = (double)__ldg(a.in[i] + off[i]);
+    double acc = v[0];
+    int next = 1;
+    for (int s = 0; s < ca.n_steps; s++) {
+        const int kind = ca.kind[s], op = ca.op[s];
+        if (kind == CH_UNARY) {
+            acc = dun(op, acc);
+            continue;
+        }
+        double other = ca.dscalar[s];
+        if (kind == CH_ACC_IN || kind == CH_IN_ACC) {
+            other = v[NIN > 1 ? 1 : 0];
+            if (NIN > 2 && next == 2) other = v[NIN > 2 ? 2 : 0];
+            if (NIN > 3 && next == 3) other = v[NIN > 3 ? 3 : 0];
+            next++;
+        }
+        acc = (kind == CH_ACC_IN || kind == CH_ACC_SCALAR) ? dbin(op, acc, other) : dbin(op, other, acc);
+    }
+    a.out[item] = (float)acc;
+}
+
 struct ChainPlan {
     int n_steps;
     unsigned char kind[kChainMaxSteps], op[kChainMaxSteps];
     float scalar[kChainMaxSteps];
+    double dscalar[kChainMaxSteps];
     bool full;
+    bool f64;
 };
 
 template <int VEC, int NIN>
@@ -319,7 +417,7 @@ static bool launch_chain_one(const ChainPlan& plan, const Folded& fo, const floa
     const bool special = VEC == 4 && !plan.full && !any_inner_bcast && rt().chain_block >= 2;
     const int rows = special ? kChainRows : kChainBlock;
     int blk = -1;
-    for (int d = 1; d < fo.ndim && rt().chain_block; d++) {
+    for (int d = 1; d < fo.ndim && rt().chain_block && !plan.f64; d++) {
         if (fo.extent[d] < (uint64_t)rows) continue;
         bool invariant = false;
         for (int i = 0; i < NIN; i++) invariant |= fo.in_stride[i][d] == 0;
@@ -361,8 +459,14 @@ static bool launch_chain_one(const ChainPlan& plan, const Folded& fo, const floa
     memcpy(ca.kind, plan.kind, sizeof ca.kind);
     memcpy(ca.op, plan.op, sizeof ca.op);
     memcpy(ca.scalar, plan.scalar, sizeof ca.scalar);
+    memcpy(ca.dscalar, plan.dscalar, sizeof ca.dscalar);
     const unsigned blocks = (unsigned)((n_items + kEwThreads - 1) / kEwThreads);
     cudaStream_t st = rt().stream;
+    if (plan.f64) {  // only reached with VEC == 1 and no blocking (see run_chain)
+        ew_chain_f64_kernel<NIN><<<blocks, kEwThreads, 0, st>>>(ca);
+        note_launch("ew_chain_f64");
+        return check_launch("ew_chain_f64");
+    }
     if (blk >= 0 && special) {
         int inv = 0;
         for (int i = 0; i < NIN; i++) inv |= (ca.blk_in[i] == 0) << i;
@@ -402,7 +506,7 @@ static bool launch_chain(const ChainPlan& plan, Folded fo, const float* const* i
 
 template <int NIN>
 static bool run_chain(const ChainPlan& plan, const Folded& fo, const float* const* in, float* out) {
-    bool vec_ok = !rt().force_general && ((uintptr_t)out % 16 == 0) && fo.extent[0] % 4 == 0;
+    bool vec_ok = !plan.f64 && !rt().force_general && ((uintptr_t)out % 16 == 0) && fo.extent[0] % 4 == 0;
     for (int i = 0; i < NIN && vec_ok; i++) {
         const int64_t s0 = fo.in_stride[i][0];
         if (s0 == 0) continue;
@@ -418,7 +522,7 @@ static bool run_chain(const ChainPlan& plan, const Folded& fo, const float* cons
 using namespace al;
 
 extern "C" NDArray* array_chain_eval(const NDArray* const* inputs, size_t n_inputs, const al_chain_step* steps,
-                                     size_t n_steps) {
+                                     size_t n_steps, int flags) {
     AL_ENTER;
     AL_REQUIRE(inputs && n_inputs >= 1 && n_inputs <= (size_t)kChainMaxInputs, "ValueError: a fused chain takes 1..%d arrays", kChainMaxInputs);
     AL_REQUIRE(n_steps <= (size_t)kChainMaxSteps && (steps || n_steps == 0), "ValueError: a fused chain holds at most %d steps", kChainMaxSteps);
@@ -448,6 +552,7 @@ extern "C" NDArray* array_chain_eval(const NDArray* const* inputs, size_t n_inpu
     ChainPlan plan;
     memset(&plan, 0, sizeof plan);
     plan.n_steps = (int)n_steps;
+    plan.f64 = (flags & AL_CHAIN_F64) != 0;
     size_t consumed = 1;
     for (size_t s = 0; s < n_steps; s++) {
         const int kind = steps[s].kind, op = steps[s].op;
@@ -462,7 +567,8 @@ extern "C" NDArray* array_chain_eval(const NDArray* const* inputs, size_t n_inpu
         }
         plan.kind[s] = (unsigned char)kind;
         plan.op[s] = (unsigned char)op;
-        plan.scalar[s] = steps[s].scalar;
+        plan.scalar[s] = (float)steps[s].scalar;
+        plan.dscalar[s] = steps[s].scalar;
     }
     AL_REQUIRE(consumed == n_inputs, "ValueError: the chain consumes %zu arrays but %zu were given", consumed, n_inputs);
     NDArray* out = new_array(shape, nd);

@@ -429,11 +429,23 @@ reduce_window_kernel(const float* __restrict__ x, float* __restrict__ out, uint3
     const size_t i0 = (size_t)blockIdx.x * tile;
     const size_t n_in = (size_t)nout + w - 1;
     const uint32_t span = tile + w;
-    for (uint32_t e = threadIdx.x; e < span; e += kWinThreads) {
-        const size_t gi = i0 + e;
-        const float v = gi < n_in ? __ldcs(x + gi) : rident<OP>();
-        const uint32_t b = e / w, k = e - b * w;
-        P[b * pitch + k] = v;
+    // stage with 8 loads in flight per thread (the loop-carried div/mod otherwise serialises them)
+    for (uint32_t e0 = 0; e0 < span; e0 += 8 * kWinThreads) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t e = e0 + u * kWinThreads + threadIdx.x;
+            const size_t gi = i0 + e;
+            v[u] = (e < span && gi < n_in) ? __ldcs(x + gi) : rident<OP>();
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t e = e0 + u * kWinThreads + threadIdx.x;
+            if (e < span) {
+                const uint32_t b = e / w, k = e - b * w;
+                P[b * pitch + k] = v[u];
+            }
+        }
     }
     __syncthreads();
     for (uint32_t b = threadIdx.x; b <= nblk; b += kWinThreads) {

@@ -21,46 +21,64 @@ MAX_ARRAYS, MAX_STEPS = 4, 8
 ACC_IN, IN_ACC, ACC_SCALAR, SCALAR_ACC, UNARY = range(5)
 
 
+CHAIN_F64 = 1
+
+
 class ChainStep(C.Structure):
-    _fields_ = [("kind", C.c_int), ("op", C.c_int), ("scalar", C.c_float)]
+    _fields_ = [("kind", C.c_int), ("op", C.c_int), ("scalar", C.c_double)]
 
 
 lib.array_chain_eval.restype = ArrayP
-lib.array_chain_eval.argtypes = [C.POINTER(ArrayP), C.c_size_t, C.POINTER(ChainStep), C.c_size_t]
+lib.array_chain_eval.argtypes = [C.POINTER(ArrayP), C.c_size_t, C.POINTER(ChainStep), C.c_size_t, C.c_int]
+
+_NP_BINARY = {"add": "sum", "subtract": "sub", "multiply": "mul", "divide": "div", "true_divide": "div", "power": "pow",
+              "maximum": "max", "minimum": "min", "fmax": "max", "fmin": "min", "less": "lt", "less_equal": "le",
+              "greater": "gt", "greater_equal": "ge", "fmod": "mod"}
+_NP_UNARY = {"negative": "neg", "absolute": "abs", "fabs": "abs", "sqrt": "sqrt", "exp": "exp", "log": "log", "sin": "sin",
+             "cos": "cos", "tan": "tan", "arcsin": "asin", "arccos": "acos", "arctan": "atan", "sinh": "sinh", "cosh": "cosh",
+             "tanh": "tanh", "arcsinh": "asinh", "arccosh": "acosh", "arctanh": "atanh", "ceil": "ceil", "floor": "floor"}
 
 
 class Expr:
     """A recorded elementwise chain over device arrays."""
 
-    __slots__ = ("arrays", "steps")
+    __slots__ = ("arrays", "steps", "f64")
+    __array_priority__ = 1000
 
-    def __init__(self, arrays, steps=()):
-        self.arrays, self.steps = list(arrays), list(steps)
+    def __init__(self, arrays, steps=(), f64=False):
+        self.arrays, self.steps, self.f64 = list(arrays), list(steps), f64
 
     # -- recording ---------------------------------------------------------------------------------
     def _flushed(self, needs_array: bool):
         """Self if it still has room for one more step (and one more array when the step consumes
         one), else a fresh chain over its evaluated value."""
         if len(self.steps) >= MAX_STEPS or (needs_array and len(self.arrays) >= MAX_ARRAYS):
+            if self.f64:  # an intermediate f32 rounding would change the result
+                raise NotImplementedError("FP64-mode chains are limited to 8 steps and 4 arrays")
             return Expr([self.eval()])
         return self
 
     def _binary(self, op: str, other, reverse: bool):
         code = BINOPS.index(op)
         if isinstance(other, Expr):
-            other = other.eval()
+            if not other.steps:          # a bare input (e.g. the `x` in `x * x`): just another operand
+                other = other.arrays[0]
+            elif self.f64 or other.f64:  # evaluating it would round an intermediate to f32
+                raise NotImplementedError("FP64-mode chains must be left-deep: (x + 1) * (x - 1) is not")
+            else:
+                other = other.eval()
         if isinstance(other, core.NDArray):
             base = self._flushed(True)
-            return Expr(base.arrays + [other], base.steps + [(IN_ACC if reverse else ACC_IN, code, 0.0)])
-        if isinstance(other, core.Number):
+            return Expr(base.arrays + [other], base.steps + [(IN_ACC if reverse else ACC_IN, code, 0.0)], self.f64)
+        if isinstance(other, core.Number) or type(other).__module__ == "numpy" and getattr(other, "ndim", 1) == 0:
             base = self._flushed(False)
-            return Expr(base.arrays, base.steps + [(SCALAR_ACC if reverse else ACC_SCALAR, code, float(other))])
+            return Expr(base.arrays, base.steps + [(SCALAR_ACC if reverse else ACC_SCALAR, code, float(other))], self.f64)
         return NotImplemented
 
     def apply(self, fn):
         from . import ufuncs
         base = self._flushed(False)
-        return Expr(base.arrays, base.steps + [(UNARY, ufuncs.resolve_unary(fn), 0.0)])
+        return Expr(base.arrays, base.steps + [(UNARY, ufuncs.resolve_unary(fn), 0.0)], self.f64)
 
     def __add__(self, o): return self._binary("sum", o, False)
     def __radd__(self, o): return self._binary("sum", o, True)
@@ -75,7 +93,33 @@ class Expr:
     def __le__(self, o): return self._binary("le", o, False)
     def __gt__(self, o): return self._binary("gt", o, False)
     def __ge__(self, o): return self._binary("ge", o, False)
+    def __rpow__(self, o): return self._binary("pow", o, True)
     def __neg__(self): return self.apply("neg")
+    def __pos__(self): return self
+    def __abs__(self): return self.apply("abs")
+    def __ceil__(self): return self.apply("ceil")
+    def __floor__(self): return self.apply("floor")
+
+    def __bool__(self):  # `if x > 0:` or builtin max/min inside a traced lambda: data dependent, not traceable
+        raise TypeError("a lazy arraylib expression has no truth value")
+
+    def __float__(self):  # math.sqrt(expr) etc.: math.* needs a real float, so tracing stops here
+        raise TypeError("a lazy arraylib expression cannot be converted to a Python float")
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        """numpy ufuncs applied to a lazy expression are recorded as chain steps."""
+        if method != "__call__" or kwargs:
+            return NotImplemented
+        name = ufunc.__name__
+        if len(inputs) == 1 and name in _NP_UNARY:
+            return self.apply(_NP_UNARY[name])
+        if len(inputs) == 2 and name in _NP_BINARY:
+            lhs, rhs = inputs
+            if lhs is self:
+                return self._binary(_NP_BINARY[name], rhs, False)
+            return self._binary(_NP_BINARY[name], lhs, True)
+        return NotImplemented
+
     def maximum(self, o): return self._binary("max", o, False)
     def minimum(self, o): return self._binary("min", o, False)
     def sqrt(self): return self.apply("sqrt")
@@ -85,10 +129,13 @@ class Expr:
     def eval(self) -> "core.NDArray":
         if not self.steps:
             return core.copy(self.arrays[0], deep=True)
+        if len(self.steps) > MAX_STEPS or len(self.arrays) > MAX_ARRAYS:
+            raise NotImplementedError("chain too long")
         n = len(self.arrays)
         ptrs = (ArrayP * n)(*[a.buffer for a in self.arrays])
         steps = (ChainStep * len(self.steps))(*[ChainStep(k, o, s) for k, o, s in self.steps])
-        return core.NDArray(check_ptr(lib.array_chain_eval(ptrs, n, steps, len(self.steps))))
+        flags = CHAIN_F64 if self.f64 else 0
+        return core.NDArray(check_ptr(lib.array_chain_eval(ptrs, n, steps, len(self.steps), flags)))
 
     def __repr__(self):
         names = [f"{('acc∘in', 'in∘acc', 'acc∘s', 's∘acc', 'ufunc')[k]}:{(UFUNCS if k == UNARY else BINOPS)[o]}" for k, o, _ in self.steps]
@@ -98,6 +145,19 @@ class Expr:
 def lazy(array) -> Expr:
     assert isinstance(array, core.NDArray)
     return Expr([array])
+
+
+def trace_unary(fn, array):
+    """Try to record `fn` (a Python callable of one scalar) as an FP64-mode chain over `array`:
+    arithmetic operators, comparisons, abs/neg/ceil/floor and numpy ufuncs trace; `math.*` calls,
+    branches on the value and anything else do not. Returns the evaluated NDArray or None."""
+    try:
+        out = fn(Expr([array], f64=True))
+    except (TypeError, NotImplementedError, AttributeError):
+        return None
+    if isinstance(out, Expr) and out.f64 and out.arrays and all(a is array for a in out.arrays):
+        return out.eval()
+    return None
 
 
 def fused(fn, *arrays):

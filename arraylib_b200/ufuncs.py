@@ -70,6 +70,15 @@ def _by_name(fn, table):
     return name if name in table else None
 
 
+def resolve_by_name(fn):
+    """Index into al_ufunc when `fn` is a known function object or name, else None (no probing)."""
+    if isinstance(fn, str):
+        name = _ALIASES.get(fn, fn)
+        return UFUNCS.index(name) if name in UFUNCS else None
+    name = _by_name(fn, UFUNCS)
+    return UFUNCS.index(name) if name is not None else None
+
+
 def resolve_unary(fn) -> int:
     """Index into al_ufunc for `fn`, or NotImplementedError."""
     if isinstance(fn, str):

@@ -56,7 +56,7 @@ def test_chain_errors(al):
     with pytest.raises(ValueError):
         (al.lazy(al.ones((2, 3))) + al.ones((4,))).eval()
     with pytest.raises(NotImplementedError):
-        al.lazy(al.ones((2, 3))).apply(lambda v: v * v + 1.0)
+        al.lazy(al.ones((2, 3))).apply(lambda v: math.sqrt(v) + 1.0)
 
 
 @pytest.mark.parametrize("shapes", [((37, 1, 64), (1, 29, 64), (64,), (37, 29, 64)), ((19, 24), (24,), (19, 1), (1, 24)),
@@ -79,3 +79,43 @@ def test_four_operand_chains_all_kernels_agree(al, orc, rng, shapes):
         assert_bit_equal(al.to_numpy(got), eager, f"chain_block={mode}")
     if len(set(shapes)) > 1:  # identical contiguous operands fold to a 1-D stream: nothing to block
         assert len(seen) >= 2, seen
+
+
+@pytest.mark.parametrize("fn", [
+    lambda x: 2 * x * x + 1, lambda x: x / 3 - 0.1, lambda x: (x + 1.5) ** 2, lambda x: 1 / (1 + x * x),
+    lambda x: abs(x - 2.5) * -1.0, lambda x: np.sqrt(x * x + 1e-3), lambda x: (x > 0.25) * x,
+    lambda x: math.floor(x * 4) / 4, lambda x: np.maximum(x, 0.0) * 0.99 + x,
+])
+def test_apply_traces_arithmetic_lambdas_in_fp64(al, rng, fn):
+    """apply(lambda) = the reference's callback arithmetic: the lambda sees a Python float (double) and
+    its double result is rounded to f32 once (core.py:455-460). Exactly rounded ops => bit-exact."""
+    from arraylib_b200._lib import lib
+    x = rng.standard_normal(4000).astype(np.float32)
+    got = al.to_numpy(al.apply(fn, al.from_numpy(x)))
+    assert lib.al_last_kernel() == b"ew_chain_f64"
+    want = np.array([float(fn(float(v))) for v in x], dtype=np.float64).astype(np.float32)
+    assert_bit_equal(got, want, "traced lambda")
+
+
+def test_apply_traced_transcendentals_within_one_ulp(al, rng):
+    x = (rng.standard_normal(4000) * 2).astype(np.float32)
+    fn = lambda v: np.exp(-v * v / 2) / 2.5066282746310002  # noqa: E731
+    got = al.to_numpy(al.apply(fn, al.from_numpy(x)))
+    want = np.array([float(fn(float(v))) for v in x], dtype=np.float64).astype(np.float32)
+    ulp = np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 1 and (ulp != 0).mean() < 1e-3
+
+
+def test_apply_resolution_order_and_refusals(al):
+    a = al.arange(1, 25).reshape((4, 6))
+    from arraylib_b200._lib import lib
+    al.apply(math.sqrt, a)
+    assert lib.al_last_kernel() in (b"ew_nd_vec4", b"ew_nd_scalar")  # named ufunc, not a chain
+    al.apply(lambda v: math.sqrt(v), a)  # math.* cannot be traced -> probe fingerprint -> named ufunc
+    assert lib.al_last_kernel() in (b"ew_nd_vec4", b"ew_nd_scalar")
+    with pytest.raises(NotImplementedError):
+        al.apply(lambda v: v if v > 3 else 0.0, a)  # data-dependent branch
+    with pytest.raises(NotImplementedError):
+        al.apply(lambda v: math.sqrt(v) + 1.0, a)  # math.* inside a composite expression
+    with pytest.raises(NotImplementedError):
+        al.apply(lambda v: (v + 1) * (v - 1), a)  # not a left-deep chain (would need an intermediate)
