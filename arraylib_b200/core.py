@@ -488,9 +488,9 @@ floor = generate_unary_op("floor")
 def apply(fn, array) -> NDArray:
     """Elementwise map on the device. `fn` is resolved, in this order, to
       1. a named device ufunc by identity / name (math.sqrt, np.log, abs, ...);
-      2. a traced chain: arithmetic lambdas such as `lambda x: 2 * x * x + 1` or `lambda x: np.exp(-x)`
-         are recorded on a lazy proxy and run as one FP64-mode kernel (double arithmetic, one final
-         rounding: the arithmetic of the reference's per-element Python callback);
+      2. a traced FP64 tape: arithmetic lambdas such as `lambda x: 2 * x * x + 1`, `lambda x: (x + 1) / (x - 1)`
+         or `lambda x: np.exp(-x * x)` are recorded on a scalar proxy and run as one kernel in double
+         precision with one final rounding (the arithmetic of the reference's per-element Python callback);
       3. a named device ufunc by probe fingerprint (e.g. `lambda x: math.sqrt(x)`).
     Anything else raises NotImplementedError -- there is no CPU fallback."""
     assert callable(fn) or isinstance(fn, str)

@@ -27,7 +27,6 @@ struct ChainArgs {
     unsigned char kind[kChainMaxSteps];
     unsigned char op[kChainMaxSteps];
     float scalar[kChainMaxSteps];
-    double dscalar[kChainMaxSteps];  // the same constants at full precision (FP64 mode)
 };
 
 // One chain step over N lanes. The op is decoded ONCE (the switch is outside the lane loops), so the
@@ -299,7 +298,7 @@ static void launch_blocked_inv(const ChainArgs<NIN>& ca, unsigned blocks, int in
     }
 }
 
-// ---- FP64 mode: the chain runs in double precision and rounds to f32 ONCE at the end -------------------
+// ---- FP64 evaluation: compute in double precision and round to f32 ONCE at the end ------------------------
 // This is the arithmetic of the reference's `apply(fn)`: cffi hands the Python callback a C float
 // widened to a Python float (a double), the lambda computes in double, and the returned double is
 // narrowed to f32 (/root/reference/arraylib/core.py:455-460, arraylib.c:638-645). A traced lambda
@@ -347,60 +346,63 @@ __device__ __forceinline__ double dun(int op, double x) {
     }
 }
 
-template <int NIN>
-__global__ void __launch_bounds__(kEwThreads) ew_chain_f64_kernel(const ChainArgs<NIN> ca) {
-    const NdArgs<NIN>& a = ca.nd;
+// ---- FP64 tape: a small register machine for traced apply() lambdas ---------------------------------------
+constexpr int kTapeMax = 32;
+constexpr int kTapeConst = -100;  // operand source: the instruction's own constant
+
+struct TapeArgs {
+    float* out;
+    const float* in[kChainMaxInputs];
+    long long stride[kChainMaxInputs][kMaxDims];
+    uint32_t n_items;
+    int ndim, n_in, n_insn, result;
+    uint32_t extent[kMaxDims];
+    FastDiv div[kMaxDims];
+    unsigned char kind[kTapeMax], op[kTapeMax];
+    signed char a_src[kTapeMax], b_src[kTapeMax];
+    double a_const[kTapeMax], b_const[kTapeMax];
+};
+
+#pragma nv_diag_suppress 549  // r[] is written by instruction s before any later instruction may read it (validated on the host)
+__global__ void __launch_bounds__(kEwThreads) ew_tape_f64_kernel(const __grid_constant__ TapeArgs t) {
     const uint32_t item = blockIdx.x * (uint32_t)kEwThreads + threadIdx.x;
-    if (item >= a.n_items) return;
-    long long off[NIN];
-#pragma unroll
-    for (int i = 0; i < NIN; i++) off[i] = 0;
+    if (item >= t.n_items) return;
+    long long off[kChainMaxInputs] = {0, 0, 0, 0};
     uint32_t rem = item;
-#pragma unroll
-    for (int d = 0; d < kMaxDims; d++) {
+    for (int d = 0; d < t.ndim; d++) {
         uint32_t idx;
-        const bool last = (d == a.ndim - 1);
-        if (last) {
+        if (d == t.ndim - 1) {
             idx = rem;
         } else {
-            const uint32_t q = fdiv(rem, a.div[d]);
-            idx = rem - q * a.extent[d];
+            const uint32_t q = fdiv(rem, t.div[d]);
+            idx = rem - q * t.extent[d];
             rem = q;
         }
 #pragma unroll
-        for (int i = 0; i < NIN; i++) off[i] += (long long)idx * a.stride[i][d];
-        if (last) break;
+        for (int i = 0; i < kChainMaxInputs; i++) off[i] += (long long)idx * t.stride[i][d];
     }
-    double v[NIN];
+    double in[kChainMaxInputs];
 #pragma unroll
-    for (int i = 0; i < NIN; i++) v[i] = (double)__ldg(a.in[i] + off[i]);
-    double acc = v[0];
-    int next = 1;
-    for (int s = 0; s < ca.n_steps; s++) {
-        const int kind = ca.kind[s], op = ca.op[s];
-        if (kind == CH_UNARY) {
-            acc = dun(op, acc);
-            continue;
-        }
-        double other = ca.dscalar[s];
-        if (kind == CH_ACC_IN || kind == CH_IN_ACC) {
-            other = v[NIN > 1 ? 1 : 0];
-            if (NIN > 2 && next == 2) other = v[NIN > 2 ? 2 : 0];
-            if (NIN > 3 && next == 3) other = v[NIN > 3 ? 3 : 0];
-            next++;
-        }
-        acc = (kind == CH_ACC_IN || kind == CH_ACC_SCALAR) ? dbin(op, acc, other) : dbin(op, other, acc);
+    for (int i = 0; i < kChainMaxInputs; i++) in[i] = i < t.n_in ? (double)__ldg(t.in[i] + off[i]) : 0.0;
+    double r[kTapeMax];  // register file of the tape (dynamic indexing -> L1-resident local memory)
+    auto fetch = [&](int src, double c) -> double {
+        if (src >= 0) return r[src];
+        if (src == kTapeConst) return c;
+        const int i = -1 - src;
+        return i == 0 ? in[0] : i == 1 ? in[1] : i == 2 ? in[2] : in[3];
+    };
+    for (int s = 0; s < t.n_insn; s++) {
+        const double a = fetch(t.a_src[s], t.a_const[s]);
+        r[s] = t.kind[s] ? dun(t.op[s], a) : dbin(t.op[s], a, fetch(t.b_src[s], t.b_const[s]));
     }
-    a.out[item] = (float)acc;
+    t.out[item] = (float)r[t.result];
 }
 
 struct ChainPlan {
     int n_steps;
     unsigned char kind[kChainMaxSteps], op[kChainMaxSteps];
     float scalar[kChainMaxSteps];
-    double dscalar[kChainMaxSteps];
     bool full;
-    bool f64;
 };
 
 template <int VEC, int NIN>
@@ -417,7 +419,7 @@ static bool launch_chain_one(const ChainPlan& plan, const Folded& fo, const floa
     const bool special = VEC == 4 && !plan.full && !any_inner_bcast && rt().chain_block >= 2;
     const int rows = special ? kChainRows : kChainBlock;
     int blk = -1;
-    for (int d = 1; d < fo.ndim && rt().chain_block && !plan.f64; d++) {
+    for (int d = 1; d < fo.ndim && rt().chain_block; d++) {
         if (fo.extent[d] < (uint64_t)rows) continue;
         bool invariant = false;
         for (int i = 0; i < NIN; i++) invariant |= fo.in_stride[i][d] == 0;
@@ -459,14 +461,8 @@ static bool launch_chain_one(const ChainPlan& plan, const Folded& fo, const floa
     memcpy(ca.kind, plan.kind, sizeof ca.kind);
     memcpy(ca.op, plan.op, sizeof ca.op);
     memcpy(ca.scalar, plan.scalar, sizeof ca.scalar);
-    memcpy(ca.dscalar, plan.dscalar, sizeof ca.dscalar);
     const unsigned blocks = (unsigned)((n_items + kEwThreads - 1) / kEwThreads);
     cudaStream_t st = rt().stream;
-    if (plan.f64) {  // only reached with VEC == 1 and no blocking (see run_chain)
-        ew_chain_f64_kernel<NIN><<<blocks, kEwThreads, 0, st>>>(ca);
-        note_launch("ew_chain_f64");
-        return check_launch("ew_chain_f64");
-    }
     if (blk >= 0 && special) {
         int inv = 0;
         for (int i = 0; i < NIN; i++) inv |= (ca.blk_in[i] == 0) << i;
@@ -506,7 +502,7 @@ static bool launch_chain(const ChainPlan& plan, Folded fo, const float* const* i
 
 template <int NIN>
 static bool run_chain(const ChainPlan& plan, const Folded& fo, const float* const* in, float* out) {
-    bool vec_ok = !plan.f64 && !rt().force_general && ((uintptr_t)out % 16 == 0) && fo.extent[0] % 4 == 0;
+    bool vec_ok = !rt().force_general && ((uintptr_t)out % 16 == 0) && fo.extent[0] % 4 == 0;
     for (int i = 0; i < NIN && vec_ok; i++) {
         const int64_t s0 = fo.in_stride[i][0];
         if (s0 == 0) continue;
@@ -522,7 +518,7 @@ static bool run_chain(const ChainPlan& plan, const Folded& fo, const float* cons
 using namespace al;
 
 extern "C" NDArray* array_chain_eval(const NDArray* const* inputs, size_t n_inputs, const al_chain_step* steps,
-                                     size_t n_steps, int flags) {
+                                     size_t n_steps) {
     AL_ENTER;
     AL_REQUIRE(inputs && n_inputs >= 1 && n_inputs <= (size_t)kChainMaxInputs, "ValueError: a fused chain takes 1..%d arrays", kChainMaxInputs);
     AL_REQUIRE(n_steps <= (size_t)kChainMaxSteps && (steps || n_steps == 0), "ValueError: a fused chain holds at most %d steps", kChainMaxSteps);
@@ -552,7 +548,6 @@ extern "C" NDArray* array_chain_eval(const NDArray* const* inputs, size_t n_inpu
     ChainPlan plan;
     memset(&plan, 0, sizeof plan);
     plan.n_steps = (int)n_steps;
-    plan.f64 = (flags & AL_CHAIN_F64) != 0;
     size_t consumed = 1;
     for (size_t s = 0; s < n_steps; s++) {
         const int kind = steps[s].kind, op = steps[s].op;
@@ -567,8 +562,7 @@ extern "C" NDArray* array_chain_eval(const NDArray* const* inputs, size_t n_inpu
         }
         plan.kind[s] = (unsigned char)kind;
         plan.op[s] = (unsigned char)op;
-        plan.scalar[s] = (float)steps[s].scalar;
-        plan.dscalar[s] = steps[s].scalar;
+        plan.scalar[s] = steps[s].scalar;
     }
     AL_REQUIRE(consumed == n_inputs, "ValueError: the chain consumes %zu arrays but %zu were given", consumed, n_inputs);
     NDArray* out = new_array(shape, nd);
@@ -585,6 +579,91 @@ extern "C" NDArray* array_chain_eval(const NDArray* const* inputs, size_t n_inpu
             case 3: ok = run_chain<3>(plan, fo, in, out->ptr); break;
             default: ok = run_chain<4>(plan, fo, in, out->ptr); break;
         }
+    }
+    if (!ok) {
+        std::string keep = last_error_string();
+        array_free(out);
+        restore_error(keep);
+        return nullptr;
+    }
+    return out;
+}
+
+extern "C" NDArray* array_tape_eval_f64(const NDArray* const* inputs, size_t n_inputs, const al_tape_insn* tape,
+                                        size_t n_insn, size_t result) {
+    AL_ENTER;
+    AL_REQUIRE(inputs && n_inputs >= 1 && n_inputs <= (size_t)kChainMaxInputs, "ValueError: a tape takes 1..%d arrays", kChainMaxInputs);
+    AL_REQUIRE(tape && n_insn >= 1 && n_insn <= (size_t)kTapeMax, "NotImplementedError: a tape holds 1..%d instructions", kTapeMax);
+    AL_REQUIRE(result < n_insn, "ValueError: tape result index out of range");
+    size_t nd = 0;
+    for (size_t i = 0; i < n_inputs; i++) {
+        if (!valid(inputs[i], "array_tape_eval_f64")) return nullptr;
+        if (inputs[i]->lay->ndim > nd) nd = inputs[i]->lay->ndim;
+    }
+    AL_REQUIRE(nd <= 64, "ValueError: too many dimensions");
+    size_t shape[64], strides[kChainMaxInputs][64];
+    for (size_t k = 0; k < nd; k++) {
+        size_t e = 1;
+        for (size_t i = 0; i < n_inputs; i++) {
+            const Layout* l = inputs[i]->lay;
+            const size_t ei = k < l->ndim ? l->shape[l->ndim - 1 - k] : 1;
+            AL_REQUIRE(ei == e || ei == 1 || e == 1, "ValueError: can not broadcast.");
+            if (ei > e) e = ei;
+        }
+        shape[nd - 1 - k] = e;
+        for (size_t i = 0; i < n_inputs; i++) {
+            const Layout* l = inputs[i]->lay;
+            const bool present = k < l->ndim && l->shape[l->ndim - 1 - k] == e;
+            strides[i][nd - 1 - k] = present ? l->stride[l->ndim - 1 - k] : 0;
+        }
+    }
+    TapeArgs t;
+    memset(&t, 0, sizeof t);
+    for (size_t s = 0; s < n_insn; s++) {
+        const al_tape_insn& in = tape[s];
+        AL_REQUIRE(in.kind == 0 || in.kind == 1, "ValueError: unknown tape instruction kind %d", in.kind);
+        AL_REQUIRE(in.op >= 0 && in.op < (in.kind ? (int)AL_UFUNC_COUNT : (int)AL_BINOP_COUNT), "ValueError: unknown tape op %d", in.op);
+        const int srcs[2] = {in.a_src, in.kind ? kTapeConst : in.b_src};
+        for (int src : srcs)
+            AL_REQUIRE(src == kTapeConst || (src >= 0 && (size_t)src < s) || (src < 0 && src >= -(int)n_inputs),
+                       "ValueError: tape instruction %zu reads an undefined operand %d", s, src);
+        t.kind[s] = (unsigned char)in.kind;
+        t.op[s] = (unsigned char)in.op;
+        t.a_src[s] = (signed char)in.a_src;
+        t.b_src[s] = (signed char)(in.kind ? kTapeConst : in.b_src);
+        t.a_const[s] = in.a_const;
+        t.b_const[s] = in.b_const;
+    }
+    NDArray* out = new_array(shape, nd);
+    if (!out) return nullptr;
+    Folded fo;
+    const size_t* sp[kChainMaxInputs];
+    for (size_t i = 0; i < n_inputs; i++) sp[i] = strides[i];
+    bool ok = fold_layout(nd, shape, out->lay->stride, (int)n_inputs, sp, &fo);
+    uint64_t total = 1;
+    if (ok) {
+        for (int d = 0; d < fo.ndim; d++) total *= fo.extent[d];
+        if (total >= (1ull << 31)) {
+            set_error("NotImplementedError: FP64 tapes are limited to 2^31-1 elements per call");
+            ok = false;
+        }
+    }
+    if (ok) {
+        t.out = out->ptr;
+        t.n_items = (uint32_t)total;
+        t.ndim = fo.ndim;
+        t.n_in = (int)n_inputs;
+        t.n_insn = (int)n_insn;
+        t.result = (int)result;
+        for (int d = 0; d < fo.ndim; d++) {
+            t.extent[d] = (uint32_t)fo.extent[d];
+            t.div[d] = make_fastdiv(t.extent[d]);
+            for (size_t i = 0; i < n_inputs; i++) t.stride[i][d] = fo.in_stride[i][d];
+        }
+        for (size_t i = 0; i < n_inputs; i++) t.in[i] = inputs[i]->ptr;
+        ew_tape_f64_kernel<<<(unsigned)((total + kEwThreads - 1) / kEwThreads), kEwThreads, 0, rt().stream>>>(t);
+        note_launch("ew_tape_f64");
+        ok = check_launch("ew_tape_f64");
     }
     if (!ok) {
         std::string keep = last_error_string();

@@ -21,15 +21,20 @@ MAX_ARRAYS, MAX_STEPS = 4, 8
 ACC_IN, IN_ACC, ACC_SCALAR, SCALAR_ACC, UNARY = range(5)
 
 
-CHAIN_F64 = 1
-
-
 class ChainStep(C.Structure):
-    _fields_ = [("kind", C.c_int), ("op", C.c_int), ("scalar", C.c_double)]
+    _fields_ = [("kind", C.c_int), ("op", C.c_int), ("scalar", C.c_float)]
+
+
+class TapeInsn(C.Structure):
+    _fields_ = [("kind", C.c_int), ("op", C.c_int), ("a_src", C.c_int), ("b_src", C.c_int),
+                ("a_const", C.c_double), ("b_const", C.c_double)]
 
 
 lib.array_chain_eval.restype = ArrayP
-lib.array_chain_eval.argtypes = [C.POINTER(ArrayP), C.c_size_t, C.POINTER(ChainStep), C.c_size_t, C.c_int]
+lib.array_chain_eval.argtypes = [C.POINTER(ArrayP), C.c_size_t, C.POINTER(ChainStep), C.c_size_t]
+lib.array_tape_eval_f64.restype = ArrayP
+lib.array_tape_eval_f64.argtypes = [C.POINTER(ArrayP), C.c_size_t, C.POINTER(TapeInsn), C.c_size_t, C.c_size_t]
+TAPE_CONST, TAPE_MAX = -100, 32
 
 _NP_BINARY = {"add": "sum", "subtract": "sub", "multiply": "mul", "divide": "div", "true_divide": "div", "power": "pow",
               "maximum": "max", "minimum": "min", "fmax": "max", "fmin": "min", "less": "lt", "less_equal": "le",
@@ -42,19 +47,17 @@ _NP_UNARY = {"negative": "neg", "absolute": "abs", "fabs": "abs", "sqrt": "sqrt"
 class Expr:
     """A recorded elementwise chain over device arrays."""
 
-    __slots__ = ("arrays", "steps", "f64")
+    __slots__ = ("arrays", "steps")
     __array_priority__ = 1000
 
-    def __init__(self, arrays, steps=(), f64=False):
-        self.arrays, self.steps, self.f64 = list(arrays), list(steps), f64
+    def __init__(self, arrays, steps=()):
+        self.arrays, self.steps = list(arrays), list(steps)
 
     # -- recording ---------------------------------------------------------------------------------
     def _flushed(self, needs_array: bool):
         """Self if it still has room for one more step (and one more array when the step consumes
         one), else a fresh chain over its evaluated value."""
         if len(self.steps) >= MAX_STEPS or (needs_array and len(self.arrays) >= MAX_ARRAYS):
-            if self.f64:  # an intermediate f32 rounding would change the result
-                raise NotImplementedError("FP64-mode chains are limited to 8 steps and 4 arrays")
             return Expr([self.eval()])
         return self
 
@@ -63,22 +66,20 @@ class Expr:
         if isinstance(other, Expr):
             if not other.steps:          # a bare input (e.g. the `x` in `x * x`): just another operand
                 other = other.arrays[0]
-            elif self.f64 or other.f64:  # evaluating it would round an intermediate to f32
-                raise NotImplementedError("FP64-mode chains must be left-deep: (x + 1) * (x - 1) is not")
             else:
                 other = other.eval()
         if isinstance(other, core.NDArray):
             base = self._flushed(True)
-            return Expr(base.arrays + [other], base.steps + [(IN_ACC if reverse else ACC_IN, code, 0.0)], self.f64)
+            return Expr(base.arrays + [other], base.steps + [(IN_ACC if reverse else ACC_IN, code, 0.0)])
         if isinstance(other, core.Number) or type(other).__module__ == "numpy" and getattr(other, "ndim", 1) == 0:
             base = self._flushed(False)
-            return Expr(base.arrays, base.steps + [(SCALAR_ACC if reverse else ACC_SCALAR, code, float(other))], self.f64)
+            return Expr(base.arrays, base.steps + [(SCALAR_ACC if reverse else ACC_SCALAR, code, float(other))])
         return NotImplemented
 
     def apply(self, fn):
         from . import ufuncs
         base = self._flushed(False)
-        return Expr(base.arrays, base.steps + [(UNARY, ufuncs.resolve_unary(fn), 0.0)], self.f64)
+        return Expr(base.arrays, base.steps + [(UNARY, ufuncs.resolve_unary(fn), 0.0)])
 
     def __add__(self, o): return self._binary("sum", o, False)
     def __radd__(self, o): return self._binary("sum", o, True)
@@ -134,8 +135,7 @@ class Expr:
         n = len(self.arrays)
         ptrs = (ArrayP * n)(*[a.buffer for a in self.arrays])
         steps = (ChainStep * len(self.steps))(*[ChainStep(k, o, s) for k, o, s in self.steps])
-        flags = CHAIN_F64 if self.f64 else 0
-        return core.NDArray(check_ptr(lib.array_chain_eval(ptrs, n, steps, len(self.steps), flags)))
+        return core.NDArray(check_ptr(lib.array_chain_eval(ptrs, n, steps, len(self.steps))))
 
     def __repr__(self):
         names = [f"{('acc∘in', 'in∘acc', 'acc∘s', 's∘acc', 'ufunc')[k]}:{(UFUNCS if k == UNARY else BINOPS)[o]}" for k, o, _ in self.steps]
@@ -147,17 +147,109 @@ def lazy(array) -> Expr:
     return Expr([array])
 
 
-def trace_unary(fn, array):
-    """Try to record `fn` (a Python callable of one scalar) as an FP64-mode chain over `array`:
-    arithmetic operators, comparisons, abs/neg/ceil/floor and numpy ufuncs trace; `math.*` calls,
-    branches on the value and anything else do not. Returns the evaluated NDArray or None."""
-    try:
-        out = fn(Expr([array], f64=True))
-    except (TypeError, NotImplementedError, AttributeError):
+class _Trace:
+    """Shared state of one traced lambda: the input arrays and the SSA instruction list."""
+
+    def __init__(self, arrays):
+        self.arrays, self.insns = list(arrays), []
+
+    def emit(self, kind, op, a, b=None):
+        if len(self.insns) >= TAPE_MAX:
+            raise NotImplementedError("traced expression is longer than the device tape")
+        self.insns.append((kind, op, a, b))
+        return len(self.insns) - 1
+
+
+class TExpr:
+    """Scalar proxy handed to an `apply()` callable. Each arithmetic operation appends one
+    instruction to the shared FP64 tape; common sub-expressions are shared, so any expression DAG
+    (not just left-deep chains) traces. `src` is an operand reference of the tape ABI."""
+
+    __slots__ = ("trace", "src")
+    __array_priority__ = 1000
+
+    def __init__(self, trace, src):
+        self.trace, self.src = trace, src
+
+    def _operand(self, other):
+        if isinstance(other, TExpr):
+            if other.trace is not self.trace:
+                raise NotImplementedError("operands from different traces")
+            return other.src, 0.0
+        if isinstance(other, bool) or isinstance(other, core.Number) or (type(other).__module__ == "numpy" and getattr(other, "ndim", 1) == 0):
+            return TAPE_CONST, float(other)
         return None
-    if isinstance(out, Expr) and out.f64 and out.arrays and all(a is array for a in out.arrays):
-        return out.eval()
-    return None
+
+    def _binary(self, op, other, reverse):
+        operand = self._operand(other)
+        if operand is None:
+            return NotImplemented
+        mine = (self.src, 0.0)
+        a, b = (operand, mine) if reverse else (mine, operand)
+        return TExpr(self.trace, self.trace.emit(0, BINOPS.index(op), a, b))
+
+    def _unary(self, op):
+        return TExpr(self.trace, self.trace.emit(1, UFUNCS.index(op), (self.src, 0.0)))
+
+    def __add__(self, o): return self._binary("sum", o, False)
+    def __radd__(self, o): return self._binary("sum", o, True)
+    def __sub__(self, o): return self._binary("sub", o, False)
+    def __rsub__(self, o): return self._binary("sub", o, True)
+    def __mul__(self, o): return self._binary("mul", o, False)
+    def __rmul__(self, o): return self._binary("mul", o, True)
+    def __truediv__(self, o): return self._binary("div", o, False)
+    def __rtruediv__(self, o): return self._binary("div", o, True)
+    def __pow__(self, o): return self._binary("pow", o, False)
+    def __rpow__(self, o): return self._binary("pow", o, True)
+    def __lt__(self, o): return self._binary("lt", o, False)
+    def __le__(self, o): return self._binary("le", o, False)
+    def __gt__(self, o): return self._binary("gt", o, False)
+    def __ge__(self, o): return self._binary("ge", o, False)
+    def __neg__(self): return self._unary("neg")
+    def __pos__(self): return self
+    def __abs__(self): return self._unary("abs")
+    def __ceil__(self): return self._unary("ceil")
+    def __floor__(self): return self._unary("floor")
+
+    def __bool__(self):  # `if x > 0:` or builtin max/min: data dependent, cannot be traced
+        raise TypeError("a traced arraylib scalar has no truth value")
+
+    def __float__(self):  # math.sqrt(x) etc. need a real float: tracing stops here
+        raise TypeError("a traced arraylib scalar cannot be converted to a Python float")
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if method != "__call__" or kwargs:
+            return NotImplemented
+        name = ufunc.__name__
+        if len(inputs) == 1 and name in _NP_UNARY:
+            return self._unary(_NP_UNARY[name])
+        if len(inputs) == 2 and name in _NP_BINARY:
+            lhs, rhs = inputs
+            if isinstance(lhs, TExpr):
+                return lhs._binary(_NP_BINARY[name], rhs, False)
+            return self._binary(_NP_BINARY[name], lhs, True)
+        return NotImplemented
+
+
+def trace_unary(fn, array):
+    """Try to record `fn` (a Python callable of one scalar) as an FP64 tape over `array`: arithmetic
+    operators, comparisons, abs/neg/ceil/floor and numpy ufuncs trace; `math.*` calls, branches on the
+    value and anything else do not. Returns the evaluated NDArray, or None when `fn` did not trace."""
+    trace = _Trace([array])
+    try:
+        out = fn(TExpr(trace, -1))
+    except (TypeError, NotImplementedError, AttributeError, ValueError):
+        return None
+    if not isinstance(out, TExpr) or out.trace is not trace:
+        return None
+    if out.src < 0:  # the lambda returned its argument unchanged
+        return core.copy(array, deep=True)
+    insns = (TapeInsn * len(trace.insns))()
+    for i, (kind, op, a, b) in enumerate(trace.insns):
+        b = b if b is not None else (TAPE_CONST, 0.0)
+        insns[i] = TapeInsn(kind, op, a[0], b[0], a[1], b[1])
+    ptrs = (ArrayP * 1)(array.buffer)
+    return core.NDArray(check_ptr(lib.array_tape_eval_f64(ptrs, 1, insns, len(trace.insns), out.src)))
 
 
 def fused(fn, *arrays):

@@ -163,13 +163,24 @@ typedef struct {
     int kind;     /* 0: acc = binop(acc, next array)  1: acc = binop(next array, acc)
                      2: acc = binop(acc, scalar)      3: acc = binop(scalar, acc)   4: acc = ufunc(acc) */
     int op;       /* al_binop (kinds 0-3) or al_ufunc (kind 4) */
-    double scalar; /* kinds 2 and 3 (narrowed to f32 unless AL_CHAIN_F64) */
+    f32 scalar;   /* kinds 2 and 3 */
 } al_chain_step;
-enum { AL_CHAIN_F64 = 1 }; /* flags: run the chain in double precision, round to f32 once at the end
-                              (the arithmetic of the reference's apply(fn) callback, core.py:455-460) */
 /* acc starts as inputs[0]; array-consuming steps take inputs[1], inputs[2], ... in order.
  * At most 4 arrays and 8 steps; all arrays broadcast against each other (NumPy rule). */
-NDArray* array_chain_eval(const NDArray* const* inputs, size_t n_inputs, const al_chain_step* steps, size_t n_steps, int flags);
+NDArray* array_chain_eval(const NDArray* const* inputs, size_t n_inputs, const al_chain_step* steps, size_t n_steps);
+
+/* ---- FP64 tape (extension; the device form of the reference's apply(fn) Python callback, core.py:455-460:
+ *      every element is widened to double, a traced expression is evaluated in double precision and the
+ *      result is rounded to f32 once). Instruction s defines value #s; operands name an earlier value
+ *      (src >= 0), input array i (src = -1 - i) or the instruction's own constant (src = AL_TAPE_CONST). */
+enum { AL_TAPE_CONST = -100 };
+typedef struct {
+    int kind;            /* 0: value = binop(a, b)   1: value = ufunc(a) */
+    int op;              /* al_binop or al_ufunc */
+    int a_src, b_src;
+    double a_const, b_const;
+} al_tape_insn;
+NDArray* array_tape_eval_f64(const NDArray* const* inputs, size_t n_inputs, const al_tape_insn* tape, size_t n_insn, size_t result);
 
 /* ---- unary ufunc table (arraylib.c:638-665) ----------------------------------------------- */
 typedef f32 (*binop)(f32, f32);

@@ -84,6 +84,15 @@ def main():
                "asinh", "acosh", "atanh", "ceil", "floor"]:
         g[f"un_{op}"] = host(getattr(ral, op)(rx))
 
+    # ---- apply() with arithmetic callbacks (the lambda runs per element in Python double precision) ----
+    pos = np.abs(x) + np.float32(0.25)
+    pos[~np.isfinite(pos)] = np.float32(3.5)
+    g["apply_in"] = pos
+    rpos = up(pos)
+    g["apply_poly"] = host(rpos.apply(lambda v: 2 * v * v + 1))
+    g["apply_rational"] = host(rpos.apply(lambda v: 1 / (1 + v * v) - v / 3))
+    g["apply_mixed"] = host(rpos.apply(lambda v: abs(v - 2.5) * -1.0 + (v > 1.0) * v))
+
     # ---- reductions on distinct (small-integer) values, all dim subsets ---------------------------
     z = rng.integers(-8, 9, size=(4, 5, 6, 7)).astype(np.float32)
     g["red_z"] = z

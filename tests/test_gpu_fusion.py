@@ -84,7 +84,8 @@ def test_four_operand_chains_all_kernels_agree(al, orc, rng, shapes):
 @pytest.mark.parametrize("fn", [
     lambda x: 2 * x * x + 1, lambda x: x / 3 - 0.1, lambda x: (x + 1.5) ** 2, lambda x: 1 / (1 + x * x),
     lambda x: abs(x - 2.5) * -1.0, lambda x: np.sqrt(x * x + 1e-3), lambda x: (x > 0.25) * x,
-    lambda x: math.floor(x * 4) / 4, lambda x: np.maximum(x, 0.0) * 0.99 + x,
+    lambda x: math.floor(x * 4) / 4, lambda x: np.maximum(x, 0.0) + np.minimum(x, 0.0) * 0.01,
+    lambda x: (x + 1) * (x - 1) / (x * x + 2), lambda x: 1 / (1 + x * x) - x / 3,
 ])
 def test_apply_traces_arithmetic_lambdas_in_fp64(al, rng, fn):
     """apply(lambda) = the reference's callback arithmetic: the lambda sees a Python float (double) and
@@ -92,7 +93,7 @@ def test_apply_traces_arithmetic_lambdas_in_fp64(al, rng, fn):
     from arraylib_b200._lib import lib
     x = rng.standard_normal(4000).astype(np.float32)
     got = al.to_numpy(al.apply(fn, al.from_numpy(x)))
-    assert lib.al_last_kernel() == b"ew_chain_f64"
+    assert lib.al_last_kernel() == b"ew_tape_f64"
     want = np.array([float(fn(float(v))) for v in x], dtype=np.float64).astype(np.float32)
     assert_bit_equal(got, want, "traced lambda")
 
@@ -117,5 +118,13 @@ def test_apply_resolution_order_and_refusals(al):
         al.apply(lambda v: v if v > 3 else 0.0, a)  # data-dependent branch
     with pytest.raises(NotImplementedError):
         al.apply(lambda v: math.sqrt(v) + 1.0, a)  # math.* inside a composite expression
-    with pytest.raises(NotImplementedError):
-        al.apply(lambda v: (v + 1) * (v - 1), a)  # not a left-deep chain (would need an intermediate)
+
+
+def test_apply_lambdas_against_reference_golden(al):
+    """Outputs of the UNMODIFIED reference's apply(lambda) (tests/golden/make_golden.py), bit for bit."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+    X = al.from_numpy(gold["apply_in"])
+    assert_bit_equal(al.to_numpy(X.apply(lambda v: 2 * v * v + 1)), gold["apply_poly"], "poly")
+    assert_bit_equal(al.to_numpy(X.apply(lambda v: 1 / (1 + v * v) - v / 3)), gold["apply_rational"], "rational")
+    assert_bit_equal(al.to_numpy(X.apply(lambda v: abs(v - 2.5) * -1.0 + (v > 1.0) * v)), gold["apply_mixed"], "mixed")
