@@ -68,9 +68,6 @@ def algorithmic_bytes(sh):
     }
 
 
-OPS = list(algorithmic_bytes(suite_shapes(1)).keys())
-
-
 # ---------------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------------
