@@ -319,7 +319,9 @@ __device__ __forceinline__ float rfinal_fast(float init, float v, bool init_is_i
 template <int OP, int W>
 __global__ void __launch_bounds__(kWinFixedThreads, 4)
 reduce_window_fixed_kernel(const float* __restrict__ x, float* __restrict__ out, uint32_t nout, uint32_t n_tiles,
-                           float init, int init_is_identity) {
+                           uint32_t tiles_per_row, long long row_stride, float init, int init_is_identity) {
+    // `nout` windows per row; rows (a batch of independent signals) are `row_stride` source elements
+    // apart and nout outputs apart; tiles are numbered row-major over (row, tile within row).
     extern __shared__ float wsm[];
     constexpr int T = kWinFixedThreads, SPAN = kWinFixedThreads * kWinLoads;
     constexpr int PITCH = W + 1, NBLK = SPAN / W, TILE = SPAN - W, PER_THREAD = 64 / W;
@@ -345,8 +347,9 @@ reduce_window_fixed_kernel(const float* __restrict__ x, float* __restrict__ out,
     // memory, so they are in flight during the whole scan/emit work of tile k.
     float v[kWinLoads];
     auto fetch = [&](uint32_t tile) {
-        const size_t i0 = (size_t)tile * TILE;
-        const float* src = x + i0 + tid;
+        const uint32_t row = tile / tiles_per_row;
+        const size_t i0 = (size_t)(tile - row * tiles_per_row) * TILE;
+        const float* src = x + (long long)row * row_stride + i0 + tid;
         if (i0 + SPAN <= n_in) {  // CTA-uniform fast path: no per-element bounds checks
 #pragma unroll
             for (int u = 0; u < kWinLoads; u++) v[u] = __ldcs(src + u * T);
@@ -394,8 +397,9 @@ reduce_window_fixed_kernel(const float* __restrict__ x, float* __restrict__ out,
         }
         __syncthreads();
         // output e = u*T + tid: S[b][kk] (+) P[b+1][kk-1], b = u*T/W + tid/W
-        const size_t i0 = (size_t)tile * TILE;
-        float* dst = out + i0 + tid;
+        const uint32_t row = tile / tiles_per_row;
+        const size_t i0 = (size_t)(tile - row * tiles_per_row) * TILE;
+        float* dst = out + (size_t)row * nout + i0 + tid;
         if (i0 + TILE <= nout) {
 #pragma unroll
             for (int u = 0; u < kWinLoads; u++) {
@@ -478,7 +482,7 @@ reduce_window_kernel(const float* __restrict__ x, float* __restrict__ out, uint3
 }
 
 template <int OP, int W>
-static bool launch_window_fixed(const float* src, float* out, uint32_t nout, float init) {
+static bool launch_window_fixed(const float* src, float* out, uint32_t nout, uint32_t rows, long long row_stride, float init) {
     const float ident_tab[AL_REDOP_COUNT] = {0.0f, -INFINITY, INFINITY, 1.0f};
     const int init_is_identity = memcmp(&init, &ident_tab[OP], sizeof(float)) == 0;
     constexpr int kWinSpan = kWinFixedThreads * kWinLoads;
@@ -491,11 +495,14 @@ static bool launch_window_fixed(const float* src, float* out, uint32_t nout, flo
             return false;
         configured = true;
     }
-    const unsigned n_tiles = (unsigned)(((uint64_t)nout + TILE - 1) / TILE);
+    const unsigned tiles_per_row = (unsigned)(((uint64_t)nout + TILE - 1) / TILE);
+    const uint64_t all_tiles = (uint64_t)tiles_per_row * rows;
+    if (all_tiles >= (1ull << 31)) return set_error("NotImplementedError: too many window tiles"), false;
+    const unsigned n_tiles = (unsigned)all_tiles;
     const long per_sm = rt().window_ctas_per_sm > 0 ? rt().window_ctas_per_sm : 16;  // 4 resident, the rest queue (tail balance)
     unsigned blocks = (unsigned)(kNumSMs * per_sm);
     if (blocks > n_tiles) blocks = n_tiles;
-    reduce_window_fixed_kernel<OP, W><<<blocks, kWinFixedThreads, smem, rt().stream>>>(src, out, nout, n_tiles, init, init_is_identity);
+    reduce_window_fixed_kernel<OP, W><<<blocks, kWinFixedThreads, smem, rt().stream>>>(src, out, nout, n_tiles, tiles_per_row, row_stride, init, init_is_identity);
     note_launch("reduce_window");
     return check_launch("reduce_window");
 }
@@ -547,17 +554,23 @@ static bool run_reduce(const float* src, float* out, const AxisList& K, const Ax
     a.nr = R.n;
     const bool general = r.force_general;
 
-    // -- overlapping windows (C5a) --
-    if (!general && !r.disable_window && K.n == 1 && R.n == 1 && K.stride[0] == 1 && R.stride[0] == 1 &&
-        R.extent[0] >= 8 && R.extent[0] <= 1024 && nout >= 4 * R.extent[0]) {
+    // -- overlapping windows (C5a): kept stride == reduced stride == 1, optionally a batch of rows --
+    const bool win_axes = R.n == 1 && R.stride[0] == 1 && (K.n == 1 || K.n == 2) && K.stride[0] == 1;
+    if (!general && !r.disable_window && win_axes && R.extent[0] >= 8 && R.extent[0] <= 1024 && K.extent[0] >= 4 * R.extent[0]) {
         const uint32_t w = (uint32_t)R.extent[0];
+        const uint32_t per_row = (uint32_t)K.extent[0];
+        const uint32_t rows = K.n == 2 ? (uint32_t)K.extent[1] : 1;
+        const long long row_stride = K.n == 2 ? K.stride[1] : 0;
         switch (w) {
-            case 8: return launch_window_fixed<OP, 8>(src, out, (uint32_t)nout, init);
-            case 16: return launch_window_fixed<OP, 16>(src, out, (uint32_t)nout, init);
-            case 32: return launch_window_fixed<OP, 32>(src, out, (uint32_t)nout, init);
-            case 64: return launch_window_fixed<OP, 64>(src, out, (uint32_t)nout, init);
+            case 8: return launch_window_fixed<OP, 8>(src, out, per_row, rows, row_stride, init);
+            case 16: return launch_window_fixed<OP, 16>(src, out, per_row, rows, row_stride, init);
+            case 32: return launch_window_fixed<OP, 32>(src, out, per_row, rows, row_stride, init);
+            case 64: return launch_window_fixed<OP, 64>(src, out, per_row, rows, row_stride, init);
             default: break;
         }
+    }
+    if (!general && !r.disable_window && win_axes && K.n == 1 && R.extent[0] >= 8 && R.extent[0] <= 1024 && nout >= 4 * R.extent[0]) {
+        const uint32_t w = (uint32_t)R.extent[0];
         uint32_t nblk = 8192 / w;  // ~8K outputs per CTA
         if (nblk < 1) nblk = 1;
         size_t smem = 2ull * (nblk + 1) * (w + 1) * sizeof(float);

@@ -132,6 +132,20 @@ def test_sliding_window_view(al, orc, rng, n, w):
     assert np.all(err <= sum_tolerance(fn_, (1,)))
 
 
+@pytest.mark.parametrize("rows,n,w", [(5, 3000, 64), (3, 9000, 16), (17, 700, 32), (2, 20000, 8)])
+def test_batched_sliding_windows(al, orc, rng, rows, n, w):
+    """A batch of independent signals, each with stride-1 windows: view (rows, n-w+1, w), strides (n, 1, 1)."""
+    from arraylib_b200._lib import lib
+    base = int_data(rng, (rows, n))
+    V = al.from_numpy(base.reshape(-1)).as_strided(shape=(rows, n - w + 1, w), stride=(n, 1, 1))
+    vn = np.lib.stride_tricks.as_strided(base, shape=(rows, n - w + 1, w), strides=(4 * n, 4, 4))
+    got = al.reduce_sum(V, dims=[2])
+    assert lib.al_last_kernel() == b"reduce_window"
+    assert got.shape == (rows, n - w + 1, 1)
+    assert_bit_equal(al.to_numpy(got), orc.reduce("sum", vn, (2,)), "batched windows")
+    assert_bit_equal(al.to_numpy(al.reduce_min(V, dims=[2])), orc.reduce("min", vn, (2,)), "batched windows min")
+
+
 def test_window_kernel_matches_generic_path(al, rng):
     from arraylib_b200._lib import lib
     base = rng.standard_normal(50000).astype(np.float32)
