@@ -28,5 +28,6 @@ for rep in range(2):
     r = a.as_strided(shape=(n - 63, 64), stride=(1, 1)).reduce_sum(dims=[1]); del r
     r = X5.transpose((1, 0)) + Y5; del r
     r = X5.transpose((1, 0)).reshape((m * m,)); del r
+    r = (al.lazy(A) + B + c).eval(); del r
 al.synchronize()
 print("profile_ops done")

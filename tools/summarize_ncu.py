@@ -1,5 +1,7 @@
-"""Turns an `ncu --set full` report (read here, no GPU needed) into profiles/<tag>_ncu_summary.md and
-profiles/traffic.json.  Usage: python tools/summarize_ncu.py gpurun_out/prof_r1.ncu-rep r1"""
+"""Turns an `ncu --set full` capture into profiles/<tag>_ncu_summary.md and profiles/traffic.json.
+Input: the .ncu-rep, or the `ncu -i <rep> --page raw --csv` export of it (the full report of the
+whole suite exceeds gpurun's 64 MiB return limit, so the export is made on the GPU box).
+Usage: python tools/summarize_ncu.py gpurun_out/prof_r1_raw.csv r1"""
 import csv
 import io
 import json
@@ -9,7 +11,10 @@ import sys
 
 rep, tag = sys.argv[1], sys.argv[2]
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+if rep.endswith(".csv"):
+    raw = open(rep).read()
+else:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
 col = {h: i for i, h in enumerate(hdr)}
@@ -46,7 +51,7 @@ for i, r in enumerate(data):
 out_md = os.path.join(root, "profiles", f"{tag}_ncu_summary.md")
 open(out_md, "w").write("\n".join(lines) + "\n")
 # per-launch DRAM traffic of the dominant kernel (bench.py's roofline.traffic): average over its launches
-dom = [v for k, vs in traffic.items() if k.startswith("ew_nd_kernel<4, 4, BinF<0>>") for v in vs]
+dom = [v for k, vs in traffic.items() if "ew_nd_kernel<4, 4" in k and "BinF<0>" in k for v in vs]
 tj = {"source": os.path.basename(rep), "ew_nd_vec4_add_bytes_per_launch": int(sum(dom) / len(dom)) if dom else None,
       "per_kernel_bytes": {k: [int(x) for x in v] for k, v in traffic.items()}}
 json.dump(tj, open(os.path.join(root, "profiles", "traffic.json"), "w"), indent=1)
