@@ -356,35 +356,21 @@ def to_numpy(array: NDArray, out=None, blocking=True):
 
 
 def host_buffer(shape):
-    """float32 numpy array backed by PINNED host memory (extension; for fast from_numpy/to_numpy
-    staging). The memory is released when the array and all its views are garbage collected."""
+    """float32 numpy array backed by PINNED host memory (extension; staging for fast or non-blocking
+    from_numpy / to_numpy). The memory is released when the array and all its views are collected."""
+    import weakref
+
     import numpy as np
 
-    n = int(np.prod(shape)) if len(tuple(shape)) else 1
+    shape = tuple(int(e) for e in shape)
+    n = int(np.prod(shape)) if shape else 1
     n_alloc = n if n > 0 else 1  # (this module rebinds max/min/abs/pow to array ops)
     ptr = lib.al_host_alloc(n_alloc * 4)
     if not ptr:
         raise_last_error()
     raw = (C.c_float * n_alloc).from_address(ptr)
-    keeper = _PinnedOwner(ptr, raw)
-    arr = np.frombuffer(keeper, dtype=np.float32, count=n).reshape(shape)
-    return arr
-
-
-class _PinnedOwner:
-    """Buffer-protocol owner of one pinned allocation; frees it when collected."""
-
-    def __init__(self, ptr, raw):
-        self._ptr, self._raw = ptr, raw
-
-    def __buffer__(self, flags):
-        return memoryview(self._raw)
-
-    def __del__(self):
-        try:
-            lib.al_host_free(self._ptr)
-        except Exception:
-            pass
+    weakref.finalize(raw, lib.al_host_free, ptr)  # every numpy view keeps `raw` alive through .base
+    return np.ctypeslib.as_array(raw)[:n].reshape(shape)
 
 
 # -------------------------------------------------------------------------------------------------

@@ -201,7 +201,7 @@ __device__ __forceinline__ float acc_collapse(const Acc<VEC>& a) {
 // TEAM in {1,2,4,8,16,32}: sub-warp teams, one output per team (grid.y splits the reduced range).
 template <int OP, int VEC, int TEAM>
 __global__ void __launch_bounds__(256) reduce_inner_kernel(const RedArgs a) {
-    const uint32_t gt = (blockIdx.x * 256u + threadIdx.x) / TEAM;  // team id == output id
+    const uint32_t gt = (uint32_t)(((uint64_t)blockIdx.x * 256u + threadIdx.x) / TEAM);  // team id == output id (64-bit: nout*TEAM may pass 2^32)
     const uint32_t lane = threadIdx.x % TEAM;
     const bool live = gt < a.nout;
     const uint32_t r0 = blockIdx.y * a.r_per_split;
