@@ -313,7 +313,7 @@ template <int OP>
 __device__ __forceinline__ float rfinal_fast(float init, float v, bool init_is_identity) {
     if (!init_is_identity) return rfinal<OP>(init, v);
     if constexpr (OP == AL_RSUM) return __fadd_rn(v, 0.0f);
-    else return v;
+    else return racc<OP>(init, v);  // one fold is enough (idempotent); it maps an all-NaN max/min to the identity
 }
 
 template <int OP, int W>
@@ -423,6 +423,103 @@ reduce_window_fixed_kernel(const float* __restrict__ x, float* __restrict__ out,
     }
 }
 
+// w = 64 variant (config C5a): like the kernel above, but a block is split between two adjacent lanes.
+// Each lane reads only its 32 elements (one shared read per element instead of two), builds the
+// prefix and suffix scans of its half in registers, swaps half totals with its partner through one
+// shuffle and adds the partner's total to the scan that crosses the middle of the block. That is 8
+// LSU operations per output instead of 9, on the pipe that bounds this kernel. Blocks are laid out
+// with a pitch of 66 floats and a one-float gap between the halves, so the 16 blocks x 2 halves a
+// warp touches fall on 32 different banks.
+template <int OP>
+__global__ void __launch_bounds__(kWinFixedThreads, 4)
+reduce_window64_kernel(const float* __restrict__ x, float* __restrict__ out, uint32_t nout, uint32_t n_tiles,
+                       uint32_t tiles_per_row, long long row_stride, float init, int init_is_identity) {
+    extern __shared__ float wsm[];
+    constexpr int W = 64, H = 32, T = kWinFixedThreads, SPAN = kWinFixedThreads * kWinLoads;
+    constexpr int PITCH = 66, NBLK = SPAN / W, TILE = SPAN - W;
+    static_assert(T == 2 * NBLK, "one lane per half block");
+    float* P = wsm;
+    float* S = wsm + NBLK * PITCH;
+    const size_t n_in = (size_t)nout + W - 1;
+    const int tid = threadIdx.x;
+    // element e = u*T + tid of a tile: block 2u + tid/64, offset kk = tid%64, stored at kk + kk/32
+    const int kk = tid & (W - 1);
+    const int slot = (tid >> 6) * PITCH + kk + (kk >> 5);
+    float* const stage = P + slot;
+    const float* const s_lane = S + slot;
+    const float* const p_lane = P + ((tid >> 6) + 1) * PITCH + (kk - 1) + ((kk - 1) >> 5);  // P[b+1][kk-1] (kk >= 1)
+    const int half = tid & 1;
+    const int scan_base = (tid >> 1) * PITCH + half * (H + 1);
+    const bool has_head = kk != 0;
+    const bool ident = init_is_identity != 0;
+
+    float v[kWinLoads];
+    auto fetch = [&](uint32_t tile) {
+        const uint32_t row = tile / tiles_per_row;
+        const size_t i0 = (size_t)(tile - row * tiles_per_row) * TILE;
+        const float* src = x + (long long)row * row_stride + i0 + tid;
+        if (i0 + SPAN <= n_in) {
+#pragma unroll
+            for (int u = 0; u < kWinLoads; u++) v[u] = __ldcs(src + u * T);
+        } else {
+#pragma unroll
+            for (int u = 0; u < kWinLoads; u++) v[u] = (i0 + u * T + tid < n_in) ? __ldcs(src + u * T) : rident<OP>();
+        }
+    };
+    uint32_t tile = blockIdx.x;
+    if (tile < n_tiles) fetch(tile);
+    for (; tile < n_tiles; tile += gridDim.x) {
+#pragma unroll
+        for (int u = 0; u < kWinLoads; u++) stage[u * 2 * PITCH] = v[u];
+        __syncthreads();
+        if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);
+        float xr[H];
+#pragma unroll
+        for (int k = 0; k < H; k++) xr[k] = P[scan_base + k];
+        __syncthreads();  // every half block is in registers before P is overwritten in place
+        float lp[H];
+        lp[0] = xr[0];
+#pragma unroll
+        for (int k = 1; k < H; k++) lp[k] = racc<OP>(lp[k - 1], xr[k]);
+        const float other = __shfl_xor_sync(0xffffffffu, lp[H - 1], 1);  // partner's half total
+        const float before = half ? other : rident<OP>();  // what precedes this half inside the block
+        const float after = half ? rident<OP>() : other;   // what follows it
+#pragma unroll
+        for (int k = 0; k < H; k++) P[scan_base + k] = racc<OP>(before, lp[k]);
+        float run = xr[H - 1];
+        S[scan_base + H - 1] = racc<OP>(run, after);
+#pragma unroll
+        for (int k = H - 2; k >= 0; k--) {
+            run = racc<OP>(xr[k], run);
+            S[scan_base + k] = racc<OP>(run, after);
+        }
+        __syncthreads();
+        const uint32_t row = tile / tiles_per_row;
+        const size_t i0 = (size_t)(tile - row * tiles_per_row) * TILE;
+        float* dst = out + (size_t)row * nout + i0 + tid;
+        if (i0 + TILE <= nout) {
+#pragma unroll
+            for (int u = 0; u < kWinLoads; u++) {
+                if (u * T + tid < TILE) {
+                    float r = s_lane[u * 2 * PITCH];
+                    if (has_head) r = racc<OP>(r, p_lane[u * 2 * PITCH]);
+                    __stcs(dst + u * T, rfinal_fast<OP>(init, r, ident));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < kWinLoads; u++) {
+                if (u * T + tid < TILE && i0 + u * T + tid < nout) {
+                    float r = s_lane[u * 2 * PITCH];
+                    if (has_head) r = racc<OP>(r, p_lane[u * 2 * PITCH]);
+                    __stcs(dst + u * T, rfinal_fast<OP>(init, r, ident));
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Any-w variant: one thread scans one block serially.
 template <int OP>
 __global__ void __launch_bounds__(kWinThreads)
@@ -487,10 +584,13 @@ static bool launch_window_fixed(const float* src, float* out, uint32_t nout, uin
     const int init_is_identity = memcmp(&init, &ident_tab[OP], sizeof(float)) == 0;
     constexpr int kWinSpan = kWinFixedThreads * kWinLoads;
     constexpr int TILE = kWinSpan - W;
-    const size_t smem = 2ull * (kWinSpan / W) * (W + 1) * sizeof(float);
+    const bool split_halves = W == 64 && !rt().window_whole_blocks;
+    const size_t smem = 2ull * (kWinSpan / W) * (split_halves ? 66 : W + 1) * sizeof(float);
     static bool configured = false;
     if (!configured) {
-        if (!cuda_ok(cudaFuncSetAttribute(reduce_window_fixed_kernel<OP, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+        if (!cuda_ok(cudaFuncSetAttribute(reduce_window_fixed_kernel<OP, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024),
+                     "cudaFuncSetAttribute") ||
+            !cuda_ok(cudaFuncSetAttribute(reduce_window64_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024),
                      "cudaFuncSetAttribute"))
             return false;
         configured = true;
@@ -499,10 +599,13 @@ static bool launch_window_fixed(const float* src, float* out, uint32_t nout, uin
     const uint64_t all_tiles = (uint64_t)tiles_per_row * rows;
     if (all_tiles >= (1ull << 31)) return set_error("NotImplementedError: too many window tiles"), false;
     const unsigned n_tiles = (unsigned)all_tiles;
-    const long per_sm = rt().window_ctas_per_sm > 0 ? rt().window_ctas_per_sm : 16;  // 4 resident, the rest queue (tail balance)
+    const long per_sm = rt().window_ctas_per_sm > 0 ? rt().window_ctas_per_sm : 32;  // 4 resident, the rest queue (tail balance)
     unsigned blocks = (unsigned)(kNumSMs * per_sm);
     if (blocks > n_tiles) blocks = n_tiles;
-    reduce_window_fixed_kernel<OP, W><<<blocks, kWinFixedThreads, smem, rt().stream>>>(src, out, nout, n_tiles, tiles_per_row, row_stride, init, init_is_identity);
+    if (split_halves)
+        reduce_window64_kernel<OP><<<blocks, kWinFixedThreads, smem, rt().stream>>>(src, out, nout, n_tiles, tiles_per_row, row_stride, init, init_is_identity);
+    else
+        reduce_window_fixed_kernel<OP, W><<<blocks, kWinFixedThreads, smem, rt().stream>>>(src, out, nout, n_tiles, tiles_per_row, row_stride, init, init_is_identity);
     note_launch("reduce_window");
     return check_launch("reduce_window");
 }

@@ -360,6 +360,7 @@ int al_set_tuning(const char* key, long value) {
     else if (k == "reduce_splits") g_rt.reduce_splits = value;
     else if (k == "disable_window") g_rt.disable_window = value;
     else if (k == "window_ctas_per_sm") g_rt.window_ctas_per_sm = value;
+    else if (k == "window_whole_blocks") g_rt.window_whole_blocks = value;
     else if (k == "tile64") g_rt.tile64 = value;
     else if (k == "tile_tq") g_rt.tile_tq = value;
     else if (k == "chain_block") g_rt.chain_block = value;

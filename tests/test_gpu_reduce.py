@@ -161,6 +161,24 @@ def test_window_kernel_matches_generic_path(al, rng):
     assert_bit_equal(fast, slow, "window vs generic")
 
 
+def test_window_half_block_and_whole_block_kernels_agree(al, orc, rng):
+    from arraylib_b200._lib import lib
+    n, w = 300000, 64
+    base = int_data(rng, (n,))
+    base[1000:1100] = np.nan  # a stretch of all-NaN windows: max/min must give the identity like the reference
+    V = al.from_numpy(base).as_strided(shape=(n - w + 1, w), stride=(1, 1))
+    vn = np.lib.stride_tricks.as_strided(base, shape=(n - w + 1, w), strides=(4, 4))
+    for op in ("sum", "max", "min"):
+        want = orc.reduce(op, vn, (1,))
+        for whole in (0, 1):
+            lib.al_set_tuning(b"window_whole_blocks", whole)
+            try:
+                got = al.to_numpy(getattr(al, f"reduce_{op}")(V, dims=[1]))
+            finally:
+                lib.al_set_tuning(b"window_whole_blocks", 0)
+            assert_bit_equal(got, want, f"{op} whole_blocks={whole}")
+
+
 @pytest.mark.parametrize("splits", [1, 2, 7, 64])
 def test_two_pass_split_is_consistent(al, orc, rng, splits):
     from arraylib_b200._lib import lib

@@ -90,10 +90,12 @@ def bench_transpose():
 def bench_window():
     n, w = 1 << 28, 64
     base = rnd((n,), 1)
-    for per_sm in (2, 3, 4, 5, 8, 16):
+    for per_sm in (8, 16, 32):
         tune(window_ctas_per_sm=per_sm)
         timed(lambda: base.as_strided(shape=(n - w + 1, w), stride=(1, 1)).reduce_sum(dims=[1]), 4 * n + 4 * (n - w + 1), f"window-64 reduce_sum 2^28 ctas/SM={per_sm}")
-    tune(window_ctas_per_sm=0)
+    tune(window_ctas_per_sm=0, window_whole_blocks=1)
+    timed(lambda: base.as_strided(shape=(n - w + 1, w), stride=(1, 1)).reduce_sum(dims=[1]), 4 * n + 4 * (n - w + 1), "window-64 reduce_sum 2^28 whole-block kernel")
+    tune(window_whole_blocks=0)
     timed(lambda: base.as_strided(shape=(n - w + 1, w), stride=(1, 1)).reduce_max(dims=[1]), 4 * n + 4 * (n - w + 1), "window-64 reduce_max 2^28")
     for w2 in (8, 16, 32, 100):
         timed(lambda: base.as_strided(shape=(n - w2 + 1, w2), stride=(1, 1)).reduce_sum(dims=[1]), 4 * n + 4 * (n - w2 + 1), f"window-{w2} reduce_sum 2^28", reps=3)
