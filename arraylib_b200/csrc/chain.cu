@@ -517,6 +517,28 @@ static bool run_chain(const ChainPlan& plan, const Folded& fo, const float* cons
     return vec_ok ? launch_chain<4, NIN>(plan, fo, in, out) : launch_chain<1, NIN>(plan, fo, in, out);
 }
 
+// Right-aligned NumPy broadcast of n layouts (arraylib.c:171-206 generalised from two operands): fills the
+// common shape and, per operand, strides that are 0 wherever the operand is broadcast.
+static bool broadcast_all(const NDArray* const* inputs, size_t n_inputs, size_t nd, size_t* shape,
+                          size_t (*strides)[64]) {
+    for (size_t k = 0; k < nd; k++) {  // k counts axes from the right
+        size_t e = 1;
+        for (size_t i = 0; i < n_inputs; i++) {
+            const Layout* l = inputs[i]->lay;
+            const size_t ei = k < l->ndim ? l->shape[l->ndim - 1 - k] : 1;
+            AL_REQUIRE(ei == e || ei == 1 || e == 1, "ValueError: can not broadcast.");
+            if (ei > e) e = ei;
+        }
+        shape[nd - 1 - k] = e;
+        for (size_t i = 0; i < n_inputs; i++) {
+            const Layout* l = inputs[i]->lay;
+            const bool present = k < l->ndim && l->shape[l->ndim - 1 - k] == e;
+            strides[i][nd - 1 - k] = present ? l->stride[l->ndim - 1 - k] : 0;
+        }
+    }
+    return true;
+}
+
 }  // namespace al
 
 using namespace al;
@@ -532,23 +554,8 @@ extern "C" NDArray* array_chain_eval(const NDArray* const* inputs, size_t n_inpu
         if (inputs[i]->lay->ndim > nd) nd = inputs[i]->lay->ndim;
     }
     AL_REQUIRE(nd <= 64, "ValueError: too many dimensions");
-    // right-aligned broadcast of all operands (arraylib.c:171-206 generalised to n layouts)
     size_t shape[64], strides[kChainMaxInputs][64];
-    for (size_t k = 0; k < nd; k++) {
-        size_t e = 1;
-        for (size_t i = 0; i < n_inputs; i++) {
-            const Layout* l = inputs[i]->lay;
-            const size_t ei = k < l->ndim ? l->shape[l->ndim - 1 - k] : 1;
-            AL_REQUIRE(ei == e || ei == 1 || e == 1, "ValueError: can not broadcast.");
-            if (ei > e) e = ei;
-        }
-        shape[nd - 1 - k] = e;
-        for (size_t i = 0; i < n_inputs; i++) {
-            const Layout* l = inputs[i]->lay;
-            const bool present = k < l->ndim && l->shape[l->ndim - 1 - k] == e;
-            strides[i][nd - 1 - k] = present ? l->stride[l->ndim - 1 - k] : 0;
-        }
-    }
+    if (!broadcast_all(inputs, n_inputs, nd, shape, strides)) return nullptr;
     ChainPlan plan;
     memset(&plan, 0, sizeof plan);
     plan.n_steps = (int)n_steps;
@@ -606,21 +613,7 @@ extern "C" NDArray* array_tape_eval_f64(const NDArray* const* inputs, size_t n_i
     }
     AL_REQUIRE(nd <= 64, "ValueError: too many dimensions");
     size_t shape[64], strides[kChainMaxInputs][64];
-    for (size_t k = 0; k < nd; k++) {
-        size_t e = 1;
-        for (size_t i = 0; i < n_inputs; i++) {
-            const Layout* l = inputs[i]->lay;
-            const size_t ei = k < l->ndim ? l->shape[l->ndim - 1 - k] : 1;
-            AL_REQUIRE(ei == e || ei == 1 || e == 1, "ValueError: can not broadcast.");
-            if (ei > e) e = ei;
-        }
-        shape[nd - 1 - k] = e;
-        for (size_t i = 0; i < n_inputs; i++) {
-            const Layout* l = inputs[i]->lay;
-            const bool present = k < l->ndim && l->shape[l->ndim - 1 - k] == e;
-            strides[i][nd - 1 - k] = present ? l->stride[l->ndim - 1 - k] : 0;
-        }
-    }
+    if (!broadcast_all(inputs, n_inputs, nd, shape, strides)) return nullptr;
     TapeArgs t;
     memset(&t, 0, sizeof t);
     for (size_t s = 0; s < n_insn; s++) {

@@ -258,6 +258,9 @@ struct TileArgs {
     long long bstride_out[kMaxDims];
     long long bstride[NIN][kMaxDims];
     unsigned char stream_store;
+    // rectangular tiles (ew_tile_rect): tile extents and the shared-memory pitch
+    uint32_t tile_q, tile_p, pitch;
+    FastDiv div_tile_q, div_tile_p;
 };
 
 constexpr int kTile = 32, kTileRows = 8;
@@ -324,6 +327,198 @@ __global__ void __launch_bounds__(kTile * kTileRows) ew_tile_kernel(const TileAr
     }
 }
 
+
+// ---- rectangular tile kernel: transposes where one of the two extents is small ----------------------------
+// [N,3] <-> [3,N] style layouts (interleaved <-> planar): a 32x32 tile would leave most lanes idle on the
+// short axis. Here the tile is tile_q x tile_p (<= 1024 elements, the short axis taken whole), threads
+// sweep it linearly: p-fastest while loading the p-major operands (coalesced reads), q-fastest while
+// emitting (coalesced writes); the odd shared-memory pitch keeps both sweeps bank-conflict free.
+constexpr int kRectElems = 1024;
+
+template <typename F>
+__global__ void __launch_bounds__(256) ew_tile_rect_kernel(const TileArgs<F::NIN> a, const F f) {
+    constexpr int NIN = F::NIN;
+    __shared__ float tile[NIN][kRectElems + kRectElems / 2];
+    uint32_t t = blockIdx.x;
+    uint32_t r = fdiv(t, a.div_tq);
+    const uint32_t tq = t - r * a.tiles_q;
+    uint32_t b = fdiv(r, a.div_tp);
+    const uint32_t tp = r - b * a.tiles_p;
+    long long obase = 0, ibase[NIN];
+#pragma unroll
+    for (int i = 0; i < NIN; i++) ibase[i] = 0;
+    for (int d = 0; d < a.nbatch; d++) {
+        uint32_t idx;
+        if (d == a.nbatch - 1) {
+            idx = b;
+        } else {
+            uint32_t q = fdiv(b, a.bdiv[d]);
+            idx = b - q * a.bext[d];
+            b = q;
+        }
+        obase += (long long)idx * a.bstride_out[d];
+#pragma unroll
+        for (int i = 0; i < NIN; i++) ibase[i] += (long long)idx * a.bstride[i][d];
+    }
+    const uint32_t q0 = tq * a.tile_q, p0 = tp * a.tile_p;
+    const uint32_t n_tile = a.tile_q * a.tile_p;
+    for (uint32_t e = threadIdx.x; e < n_tile; e += 256) {  // p fastest
+        const uint32_t ql = fdiv(e, a.div_tile_p), pl = e - ql * a.tile_p;
+        const uint32_t q = q0 + ql, p = p0 + pl;
+        if (q < a.ext_q && p < a.ext_p) {
+#pragma unroll
+            for (int i = 0; i < NIN; i++)
+                if (a.via_smem >> i & 1)
+                    tile[i][ql * a.pitch + pl] = __ldcs(a.in[i] + ibase[i] + (long long)q * a.sq[i] + (long long)p * a.sp[i]);
+        }
+    }
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < n_tile; e += 256) {  // q fastest
+        const uint32_t pl = fdiv(e, a.div_tile_q), ql = e - pl * a.tile_q;
+        const uint32_t q = q0 + ql, p = p0 + pl;
+        if (q < a.ext_q && p < a.ext_p) {
+            float x[NIN];
+#pragma unroll
+            for (int i = 0; i < NIN; i++) {
+                if (a.via_smem >> i & 1) x[i] = tile[i][ql * a.pitch + pl];
+                else x[i] = __ldg(a.in[i] + ibase[i] + (long long)q * a.sq[i] + (long long)p * a.sp[i]);
+            }
+            float* dst = a.out + obase + q + (long long)p * a.out_sp;
+            const float y = f(x);
+            if (a.stream_store) __stcs(dst, y);
+            else *dst = y;
+        }
+    }
+}
+
+// ---- packed interleave kernels: [N, C] <-> [C, N] with a short, densely packed axis C ------------------------
+// The layouts of RGB pixels, xyz points or complex pairs. Because the interleaved side is one
+// contiguous stream, it is moved with 128-bit accesses; the planar side is moved with 128-bit accesses
+// along n; only the shared-memory side of the shuffle is scalar. A CTA handles `chunk` consecutive n.
+constexpr int kIlvFloats = 4096;  // shared-memory floats per staged operand (chunk * C <= 4096)
+
+template <int NIN>
+struct IlvArgs {
+    float* out;
+    const float* in[NIN];
+    uint32_t C, N, chunk, chunks;  // short extent, long extent, n per CTA, CTAs per batch item
+    FastDiv div_c, div_chunks;
+    long long plane_in;             // staged operand: stride between planes (planar input) -- unused when interleaved
+    long long plane_out;            // output: stride between planes (planar output)
+    uint32_t staged;                // index of the operand that goes through shared memory
+    unsigned char congruent[NIN];   // other operands: 1 = same layout as the output, 0 = one broadcast scalar
+    int nbatch;
+    uint32_t bext[kMaxDims];
+    FastDiv bdiv[kMaxDims];
+    long long bstride_out[kMaxDims];
+    long long bstride[NIN][kMaxDims];
+    unsigned char stream_store;
+};
+
+template <typename F, bool PLANAR_OUT>
+__global__ void __launch_bounds__(256) ew_interleave_kernel(const IlvArgs<F::NIN> a, const F f) {
+    constexpr int NIN = F::NIN;
+    __shared__ __align__(16) float plane[kIlvFloats + 4 * 32];
+    uint32_t b = fdiv(blockIdx.x, a.div_chunks);
+    const uint32_t n0 = (blockIdx.x - b * a.chunks) * a.chunk;
+    long long obase = 0, ibase[NIN];
+#pragma unroll
+    for (int i = 0; i < NIN; i++) ibase[i] = 0;
+    for (int d = 0; d < a.nbatch; d++) {
+        uint32_t idx;
+        if (d == a.nbatch - 1) {
+            idx = b;
+        } else {
+            uint32_t q = fdiv(b, a.bdiv[d]);
+            idx = b - q * a.bext[d];
+            b = q;
+        }
+        obase += (long long)idx * a.bstride_out[d];
+#pragma unroll
+        for (int i = 0; i < NIN; i++) ibase[i] += (long long)idx * a.bstride[i][d];
+    }
+    const uint32_t len = min(a.chunk, a.N - n0);  // n handled here (a multiple of 4)
+    const uint32_t pitch = a.chunk + 4;           // floats between planes in shared memory (16-byte aligned)
+    const uint32_t stream4 = len * a.C / 4;       // float4 items of the interleaved stream
+    const float* xin = a.in[a.staged] + ibase[a.staged];
+    auto apply4 = [&](float4 x, long long other_off) -> float4 {
+        float4 o[NIN];
+#pragma unroll
+        for (int i = 0; i < NIN; i++) {
+            if ((uint32_t)i == a.staged) {
+                o[i] = x;
+            } else if (a.congruent[i]) {
+                o[i] = __ldcs(reinterpret_cast<const float4*>(a.in[i] + ibase[i] + other_off));
+            } else {
+                const float sv = __ldg(a.in[i]);
+                o[i] = make_float4(sv, sv, sv, sv);
+            }
+        }
+        float4 y;
+        float e[NIN];
+#pragma unroll
+        for (int i = 0; i < NIN; i++) e[i] = o[i].x;
+        y.x = f(e);
+#pragma unroll
+        for (int i = 0; i < NIN; i++) e[i] = o[i].y;
+        y.y = f(e);
+#pragma unroll
+        for (int i = 0; i < NIN; i++) e[i] = o[i].z;
+        y.z = f(e);
+#pragma unroll
+        for (int i = 0; i < NIN; i++) e[i] = o[i].w;
+        y.w = f(e);
+        return y;
+    };
+    if constexpr (PLANAR_OUT) {
+        // interleaved in -> planes in shared memory
+        const float4* src = reinterpret_cast<const float4*>(xin + (long long)n0 * a.C);
+        for (uint32_t v = threadIdx.x; v < stream4; v += 256) {
+            const float4 x = __ldcs(src + v);
+            uint32_t n = fdiv(4 * v, a.div_c), c = 4 * v - n * a.C;
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                plane[c * pitch + n] = xs[j];
+                if (++c == a.C) c = 0, n++;
+            }
+        }
+        __syncthreads();
+        const uint32_t per_plane = len / 4;
+        for (uint32_t v = threadIdx.x; v < per_plane * a.C; v += 256) {
+            const uint32_t c = v / per_plane, t4 = v - c * per_plane;
+            const float4 x = *reinterpret_cast<const float4*>(plane + c * pitch + 4 * t4);
+            const long long off = (long long)c * a.plane_out + n0 + 4 * t4;
+            float4* dst = reinterpret_cast<float4*>(a.out + obase + off);
+            const float4 y = apply4(x, off);
+            if (a.stream_store) __stcs(dst, y);
+            else *dst = y;
+        }
+    } else {
+        // planar in -> planes in shared memory -> interleaved stream out
+        const uint32_t per_plane = len / 4;
+        for (uint32_t v = threadIdx.x; v < per_plane * a.C; v += 256) {
+            const uint32_t c = v / per_plane, t4 = v - c * per_plane;
+            const float4 x = __ldcs(reinterpret_cast<const float4*>(xin + (long long)c * a.plane_in + n0 + 4 * t4));
+            *reinterpret_cast<float4*>(plane + c * pitch + 4 * t4) = x;
+        }
+        __syncthreads();
+        for (uint32_t v = threadIdx.x; v < stream4; v += 256) {
+            uint32_t n = fdiv(4 * v, a.div_c), c = 4 * v - n * a.C;
+            float xs[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                xs[j] = plane[c * pitch + n];
+                if (++c == a.C) c = 0, n++;
+            }
+            const long long off = (long long)n0 * a.C + 4 * v;
+            float4* dst = reinterpret_cast<float4*>(a.out + obase + off);
+            const float4 y = apply4(make_float4(xs[0], xs[1], xs[2], xs[3]), off);
+            if (a.stream_store) __stcs(dst, y);
+            else *dst = y;
+        }
+    }
+}
 
 // ---- 64x64 float4 transpose kernel (fast path of ew_tile) ---------------------------------------------
 // Every global access is 128-bit. A thread loads a 4x4 block (4 rows along q, one float4 along p),
@@ -594,6 +789,79 @@ static bool launch_nd(const F& f, Folded fo, const float* const* in_ptrs, float*
     return launch_nd<VEC, F>(f, lo, in_ptrs, out) && launch_nd<VEC, F>(f, hi, in_hi, out + a_ext * inner);
 }
 
+// Packed interleave plan for a TileArgs already filled by launch_tile: 0 = not applicable, 1 = launched,
+// -1 = error. Needs exactly one staged operand, densely packed on its interleaved side, every other
+// operand either laid out like the output or a single broadcast element, and 4-divisible extents.
+template <typename F>
+static int try_launch_interleave(const F& f, const Folded& fo, const float* const* in, float* out, int P,
+                                 const TileArgs<F::NIN>& t) {
+    constexpr int NIN = F::NIN;
+    if (!rt().interleave) return 0;
+    int staged = -1;
+    for (int i = 0; i < NIN; i++)
+        if (t.via_smem >> i & 1) {
+            if (staged >= 0) return 0;
+            staged = i;
+        }
+    if (staged < 0) return 0;
+    const bool planar_out = t.ext_p < t.ext_q;  // short axis p: operand is [n=q, c=p] interleaved, output is [c, n]
+    const uint32_t C = planar_out ? t.ext_p : t.ext_q, N = planar_out ? t.ext_q : t.ext_p;
+    if (C < 2 || C > 32 || N % 4 != 0 || N < 256) return 0;
+    // long long strides of the staged operand: (sq along q, sp == 1 along p)
+    if (planar_out) {
+        if (t.sq[staged] != (long long)C) return 0;          // interleaved input must be dense: offset = n*C + c
+        if (t.out_sp % 4 != 0) return 0;                     // planar output planes 16-byte aligned
+    } else {
+        if (t.sq[staged] % 4 != 0) return 0;                 // planar input: plane stride, 16-byte aligned
+        if (t.out_sp != (long long)C) return 0;              // interleaved output must be dense
+    }
+    if ((uintptr_t)out % 16 != 0 || (uintptr_t)in[staged] % 16 != 0) return 0;
+    IlvArgs<NIN> a;
+    memset(&a, 0, sizeof a);
+    a.out = out;
+    a.C = C;
+    a.N = N;
+    a.staged = (uint32_t)staged;
+    a.plane_in = planar_out ? 0 : t.sq[staged];
+    a.plane_out = planar_out ? t.out_sp : 0;
+    a.chunk = (uint32_t)(kIlvFloats / C / 32 * 32);
+    if (a.chunk > N) a.chunk = N;
+    a.chunks = (N + a.chunk - 1) / a.chunk;
+    a.div_c = make_fastdiv(C);
+    a.div_chunks = make_fastdiv(a.chunks);
+    a.nbatch = t.nbatch;
+    uint64_t nb = 1;
+    for (int d = 0; d < t.nbatch; d++) {
+        a.bext[d] = t.bext[d];
+        a.bdiv[d] = t.bdiv[d];
+        a.bstride_out[d] = t.bstride_out[d];
+        if (t.bstride_out[d] % 4 != 0) return 0;
+        for (int i = 0; i < NIN; i++) a.bstride[i][d] = t.bstride[i][d];
+        if (t.bstride[staged][d] % 4 != 0) return 0;
+        nb *= t.bext[d];
+    }
+    for (int i = 0; i < NIN; i++) {
+        a.in[i] = in[i];
+        if (i == staged) continue;
+        bool all_zero = t.sq[i] == 0 && t.sp[i] == 0, same = t.sq[i] == 1 && t.sp[i] == t.out_sp;
+        for (int d = 0; d < t.nbatch; d++) {
+            all_zero = all_zero && t.bstride[i][d] == 0;
+            same = same && t.bstride[i][d] == t.bstride_out[d];
+        }
+        if (same && (uintptr_t)in[i] % 16 == 0) a.congruent[i] = 1;
+        else if (all_zero) a.congruent[i] = 0;
+        else return 0;
+    }
+    a.stream_store = t.stream_store;
+    const uint64_t blocks = (uint64_t)a.chunks * nb;
+    if (blocks >= (1ull << 31)) return 0;
+    (void)fo, (void)P;
+    if (planar_out) ew_interleave_kernel<F, true><<<(unsigned)blocks, 256, 0, rt().stream>>>(a, f);
+    else ew_interleave_kernel<F, false><<<(unsigned)blocks, 256, 0, rt().stream>>>(a, f);
+    note_launch(planar_out ? "ew_deinterleave" : "ew_interleave");
+    return check_launch("ew_interleave") ? 1 : -1;
+}
+
 template <typename F>
 static bool launch_tile(const F& f, const Folded& fo, const float* const* in, float* out, int P) {
     constexpr int NIN = F::NIN;
@@ -636,7 +904,8 @@ static bool launch_tile(const F& f, const Folded& fo, const float* const* in, fl
     }
     a.stream_store = total * sizeof(float) >= (uint64_t)rt().stream_store_min_bytes;
     // 128-bit variant: every extent/stride/pointer that a float4 access touches must be 4-aligned
-    bool wide = rt().tile64 && a.ext_q % 4 == 0 && a.ext_p % 4 == 0 && (uintptr_t)out % 16 == 0;
+    const bool short_axis = a.ext_q < (uint32_t)kTile || a.ext_p < (uint32_t)kTile;  // -> rectangular tiles
+    bool wide = rt().tile64 && !short_axis && a.ext_q % 4 == 0 && a.ext_p % 4 == 0 && (uintptr_t)out % 16 == 0;
     for (int i = 0; i < NIN && wide; i++) {
         const bool smem = a.via_smem >> i & 1;
         if (!smem && a.sq[i] > 1) wide = false;                 // would need a strided gather
@@ -660,6 +929,28 @@ static bool launch_tile(const F& f, const Folded& fo, const float* const* in, fl
         else ew_tile64_kernel<F, 64><<<(unsigned)blocks64, 256, 0, rt().stream>>>(a, f);
         note_launch("ew_tile64_transpose");
         return check_launch("ew_tile64");
+    }
+    if (short_axis) {
+        const int ilv = try_launch_interleave<F>(f, fo, in, out, P, a);
+        if (ilv != 0) return ilv > 0;
+        // one extent is shorter than a 32x32 tile: take it whole and stretch the tile along the other
+        a.tile_p = a.ext_p < (uint32_t)kTile ? a.ext_p : (uint32_t)kRectElems / (a.ext_q < (uint32_t)kTile ? a.ext_q : (uint32_t)kTile);
+        a.tile_q = a.ext_q < (uint32_t)kTile ? a.ext_q : (uint32_t)kRectElems / a.tile_p;
+        if (a.tile_p > a.ext_p) a.tile_p = a.ext_p;
+        if (a.tile_q > a.ext_q) a.tile_q = a.ext_q;
+        a.pitch = a.tile_p | 1;
+        if ((uint64_t)a.tile_q * a.pitch > (uint64_t)(kRectElems + kRectElems / 2)) return false;
+        a.div_tile_p = make_fastdiv(a.tile_p);
+        a.div_tile_q = make_fastdiv(a.tile_q);
+        a.tiles_q = (a.ext_q + a.tile_q - 1) / a.tile_q;
+        a.tiles_p = (a.ext_p + a.tile_p - 1) / a.tile_p;
+        a.div_tq = make_fastdiv(a.tiles_q);
+        a.div_tp = make_fastdiv(a.tiles_p);
+        const uint64_t rblocks = (uint64_t)a.tiles_q * a.tiles_p * nb;
+        if (rblocks >= (1ull << 31)) return false;
+        ew_tile_rect_kernel<F><<<(unsigned)rblocks, 256, 0, rt().stream>>>(a, f);
+        note_launch("ew_tile_rect_transpose");
+        return check_launch("ew_tile_rect");
     }
     uint64_t blocks = (uint64_t)a.tiles_q * a.tiles_p * nb;
     if (blocks >= (1ull << 31)) return false;  // caller falls back to the scalar gather
@@ -736,7 +1027,8 @@ static bool run_functor(const F& f, const EwCall& c, const Folded& fo) {
         for (int i = 0; i < NIN; i++) {
             if (fo.in_stride[i][0] <= 1) continue;
             for (int P = 1; P < fo.ndim; P++) {
-                if (fo.in_stride[i][P] == 1 && fo.extent[P] >= 8 && fo.extent[P] < (1ull << 31) && fo.extent[0] >= 8) {
+                if (fo.in_stride[i][P] == 1 && fo.extent[P] >= 2 && fo.extent[P] < (1ull << 31) && fo.extent[0] >= 2 &&
+                    fo.extent[P] * fo.extent[0] >= 256) {
                     uint64_t nb = total / fo.extent[0] / fo.extent[P];
                     if (nb < (1ull << 31) && launch_tile<F>(f, fo, in, c.out, P)) return true;
                     if (!last_error_string().empty()) return false;

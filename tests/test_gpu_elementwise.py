@@ -179,6 +179,34 @@ def test_outer_broadcast_plan_is_used_and_exact(al, orc, rng):
     assert_bit_equal(plain, a - b, "nd kernel")
 
 
+@pytest.mark.parametrize("shape,perm", [((5000, 3), (1, 0)), ((3, 5000), (1, 0)), ((4096, 4), (1, 0)), ((2, 70000), (1, 0)),
+                                        ((64, 500, 2), (0, 2, 1)), ((9, 7, 301), (0, 2, 1)), ((31, 33), (1, 0)), ((6, 4, 5, 400), (0, 2, 3, 1)),
+                                        ((1027, 5), (1, 0)), ((16, 1 << 16), (1, 0))])
+def test_short_axis_transposes(al, rng, shape, perm):
+    """Interleaved <-> planar layouts ([N,3] <-> [3,N]): the packed interleave kernels (128-bit, when the
+    long extent is a multiple of 4) and the rectangular tile kernel must both be bit-exact."""
+    from arraylib_b200._lib import lib
+    x = rng.standard_normal(shape).astype(np.float32)
+    want = np.transpose(x, perm)
+    y = rng.standard_normal(want.shape).astype(np.float32)
+    X, Y = al.from_numpy(x), al.from_numpy(y)
+    seen = set()
+    for ilv in (1, 0):
+        lib.al_set_tuning(b"interleave", ilv)
+        try:
+            got = al.to_numpy(al.copy(X.transpose(perm), deep=True))
+            seen.add(lib.al_last_kernel())
+            assert_bit_equal(got, want, f"copy interleave={ilv}")
+            assert_bit_equal(al.to_numpy(X.transpose(perm) * Y), want * y, f"mul interleave={ilv}")
+            assert_bit_equal(al.to_numpy(Y - X.transpose(perm)), y - want, f"sub, transposed rhs, interleave={ilv}")
+            assert_bit_equal(al.to_numpy(X.transpose(perm) + 2.5), want + np.float32(2.5), f"scalar interleave={ilv}")
+        finally:
+            lib.al_set_tuning(b"interleave", 1)
+    assert b"ew_tile_rect_transpose" in seen, seen
+    if shape in ((5000, 3), (3, 5000), (4096, 4), (2, 70000), (64, 500, 2), (16, 1 << 16)):
+        assert seen & {b"ew_interleave", b"ew_deinterleave"}, seen
+
+
 def test_general_fallback_equals_fast_paths(al, rng):
     """force_general=1 routes everything through the scalar gather kernel; results must not move."""
     from arraylib_b200._lib import lib

@@ -82,7 +82,17 @@ def bench_transpose():
         timed(lambda: X.transpose((1, 0)) + Y, 12 * m * m, f"X.T + Y 16384^2 tile_tq={tq}")
         timed(lambda: X.transpose((1, 0)).reshape((m * m,)), 8 * m * m, f"X.T.reshape (strided copy) 16384^2 tile_tq={tq}")
     tune(tile_tq=64)
+    n = 1 << 26
+    for c in (2, 3, 4, 8, 16):
+        Z = rnd((n, c), 3)
+        timed(lambda: Z.transpose((1, 0)).reshape((n * c,)), 8 * n * c, f"[2^26,{c}].T copy (interleaved -> planar)", reps=3)
+        Zt = rnd((c, n), 4)
+        timed(lambda: Zt.transpose((1, 0)).reshape((n * c,)), 8 * n * c, f"[{c},2^26].T copy (planar -> interleaved)", reps=3)
+        del Z, Zt
     tune(force_general=1)
+    Z = rnd((n, 4), 3)
+    timed(lambda: Z.transpose((1, 0)).reshape((n * 4,)), 8 * n * 4, "[2^26,4].T copy (scalar gather fallback)", reps=3)
+    del Z
     timed(lambda: X.transpose((1, 0)) + Y, 12 * m * m, "X.T + Y 16384^2 (scalar gather fallback)", reps=3)
     tune(force_general=0)
 
