@@ -263,11 +263,17 @@ struct TileArgs {
     FastDiv div_tile_q, div_tile_p;
 };
 
-constexpr int kTile = 32, kTileRows = 8;
+constexpr int kTile = 32;  // extents below this use the rectangular / interleave plans
+
+// Scalar (4-byte) transpose tile for extents that are not multiples of 4: 64x64 with 16 loads in flight
+// per thread (32x32 for three-operand functors, to stay inside the 48 KB of static shared memory).
+template <int NIN>
+constexpr int scalar_tile_dim() { return NIN <= 2 ? 64 : 32; }
 
 template <typename F>
-__global__ void __launch_bounds__(kTile * kTileRows) ew_tile_kernel(const TileArgs<F::NIN> a, const F f) {
+__global__ void __launch_bounds__(256) ew_tile_kernel(const TileArgs<F::NIN> a, const F f) {
     constexpr int NIN = F::NIN;
+    constexpr int kTile = scalar_tile_dim<NIN>(), kTileRows = 256 / kTile;
     __shared__ float tile[NIN][kTile][kTile + 1];
     uint32_t t = blockIdx.x;
     uint32_t tq = t;
@@ -307,8 +313,21 @@ __global__ void __launch_bounds__(kTile * kTileRows) ew_tile_kernel(const TileAr
             }
         }
     }
-    __syncthreads();
+    // q-major operands are fetched before the barrier so their latency overlaps the staging above
     const uint32_t q = q0 + tx;
+    float direct[NIN][kTile / kTileRows];
+#pragma unroll
+    for (int i = 0; i < NIN; i++) {
+        if (!(a.via_smem >> i & 1)) {
+#pragma unroll
+            for (int j = 0; j < kTile; j += kTileRows) {
+                const uint32_t p = p0 + ty + j;
+                if (q < a.ext_q && p < a.ext_p)
+                    direct[i][j / kTileRows] = __ldg(a.in[i] + ibase[i] + (long long)q * a.sq[i] + (long long)p * a.sp[i]);
+            }
+        }
+    }
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < kTile; j += kTileRows) {
         const uint32_t p = p0 + ty + j;
@@ -317,7 +336,7 @@ __global__ void __launch_bounds__(kTile * kTileRows) ew_tile_kernel(const TileAr
 #pragma unroll
             for (int i = 0; i < NIN; i++) {
                 if (a.via_smem >> i & 1) x[i] = tile[i][tx][ty + j];
-                else x[i] = __ldg(a.in[i] + ibase[i] + (long long)q * a.sq[i] + (long long)p * a.sp[i]);
+                else x[i] = direct[i][j / kTileRows];
             }
             float* dst = a.out + obase + q + (long long)p * a.out_sp;
             const float y = f(x);
@@ -870,8 +889,9 @@ static bool launch_tile(const F& f, const Folded& fo, const float* const* in, fl
     a.out = out;
     a.ext_q = (uint32_t)fo.extent[0];
     a.ext_p = (uint32_t)fo.extent[P];
-    a.tiles_q = (a.ext_q + kTile - 1) / kTile;
-    a.tiles_p = (a.ext_p + kTile - 1) / kTile;
+    constexpr int kScalarTile = scalar_tile_dim<NIN>();
+    a.tiles_q = (a.ext_q + kScalarTile - 1) / kScalarTile;
+    a.tiles_p = (a.ext_p + kScalarTile - 1) / kScalarTile;
     a.div_tq = make_fastdiv(a.tiles_q);
     a.div_tp = make_fastdiv(a.tiles_p);
     // contiguous output strides of the folded axes
@@ -954,7 +974,7 @@ static bool launch_tile(const F& f, const Folded& fo, const float* const* in, fl
     }
     uint64_t blocks = (uint64_t)a.tiles_q * a.tiles_p * nb;
     if (blocks >= (1ull << 31)) return false;  // caller falls back to the scalar gather
-    ew_tile_kernel<F><<<(unsigned)blocks, dim3(kTile, kTileRows), 0, rt().stream>>>(a, f);
+    ew_tile_kernel<F><<<(unsigned)blocks, dim3(kScalarTile, 256 / kScalarTile), 0, rt().stream>>>(a, f);
     note_launch("ew_tile_transpose");
     return check_launch("ew_tile");
 }

@@ -82,8 +82,13 @@ def bench_transpose():
         timed(lambda: X.transpose((1, 0)) + Y, 12 * m * m, f"X.T + Y 16384^2 tile_tq={tq}")
         timed(lambda: X.transpose((1, 0)).reshape((m * m,)), 8 * m * m, f"X.T.reshape (strided copy) 16384^2 tile_tq={tq}")
     tune(tile_tq=64)
+    m2 = 16383  # odd extents: no 128-bit accesses possible -> scalar tile
+    X2, Y2 = rnd((m2, m2), 7), rnd((m2, m2), 8)
+    timed(lambda: X2.transpose((1, 0)) + Y2, 12 * m2 * m2, "X.T + Y 16383^2 (scalar tile)")
+    timed(lambda: X2.transpose((1, 0)).reshape((m2 * m2,)), 8 * m2 * m2, "X.T.reshape 16383^2 (scalar tile)")
+    del X2, Y2
     n = 1 << 26
-    for c in (2, 3, 4, 8, 16):
+    for c in (3,):
         Z = rnd((n, c), 3)
         timed(lambda: Z.transpose((1, 0)).reshape((n * c,)), 8 * n * c, f"[2^26,{c}].T copy (interleaved -> planar)", reps=3)
         Zt = rnd((c, n), 4)
