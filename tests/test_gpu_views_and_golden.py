@@ -185,3 +185,16 @@ def test_async_host_transfers(al, rng):
     for k, o in enumerate(outs):
         assert_bit_equal(o, hin * np.float32(k + 1) + np.float32(0.5), f"async {k}")
     assert_bit_equal(hout.reshape(70, 3, 1000), np.transpose(hin, (2, 0, 1)), "async transposed")
+
+
+def test_device_out_of_memory_raises_and_recovers(al):
+    """A request beyond the 180 GB of HBM raises MemoryError (the reference would abort the process);
+    the cache is handed back to the driver on the way and the library keeps working."""
+    from arraylib_b200._lib import lib
+    keep = al.ones((1 << 20,))
+    with pytest.raises(MemoryError):
+        al.zeros((1 << 36,))  # 256 GiB
+    assert lib.al_last_error().startswith(b"MemoryError")
+    assert float(al.to_numpy(al.reduce_sum(keep + 1.0)).reshape(-1)[0]) == 2.0 * (1 << 20)
+    assert lib.al_trim_pool() == 0
+    assert float(al.to_numpy(al.reduce_sum(keep)).reshape(-1)[0]) == float(1 << 20)
