@@ -198,3 +198,23 @@ def test_device_out_of_memory_raises_and_recovers(al):
     assert float(al.to_numpy(al.reduce_sum(keep + 1.0)).reshape(-1)[0]) == 2.0 * (1 << 20)
     assert lib.al_trim_pool() == 0
     assert float(al.to_numpy(al.reduce_sum(keep)).reshape(-1)[0]) == float(1 << 20)
+
+
+def test_arange_random_parameters_through_the_c_abi(al, orc):
+    """array_arange takes f32 arguments; the Python API only passes ints. Integer and non-integer
+    steps, starts near 2^24 (where the reference's f32 recurrence stops being exact), all bit-exact."""
+    from arraylib_b200._lib import lib
+    rng = np.random.default_rng(99)
+    cases = [(0, 7, 1), (3, 50, 2.5), (1, 9, 1.75), (16777210, 16777300, 1), (16777000, 16779000, 3), (5, 40000, 7.25),
+             (33554400, 33554600, 2), (33554400, 33554600, 5), (0.5, 20.5, 1), (2.75, 100, 3)]
+    for _ in range(30):
+        start = float(rng.integers(0, 1 << 25))
+        step = float(rng.choice([1, 2, 3, 5, 1.5, 2.25, 7, 16, 33]))
+        cases.append((start, start + float(rng.integers(1, 5000)), step))
+    for start, end, step in cases:
+        want = orc.arange(start, end, step)
+        got = al.NDArray(lib.array_arange(start, end, step))
+        assert got.shape == want.shape, (start, end, step)
+        assert_bit_equal(al.to_numpy(got), want, f"arange({start}, {end}, {step})")
+    for start, end, n in [(0, 10, 5), (1, 100, 10), (3, 7, 11), (0, 1, 1000), (5, 6, 3)]:
+        assert_bit_equal(al.to_numpy(al.linspace(start, end, n)), orc.linspace(start, end, n), f"linspace {start} {end} {n}")
