@@ -373,6 +373,86 @@ int al_set_tuning(const char* key, long value) {
     return 0;
 }
 
+// ---- low-level helpers the reference header also declares (arraylib.h "MEMORY ALLOCATORS", "DATA",
+//      "LAYOUT"); the reference's Python never calls them, they exist so that its cdef binds completely --
+void* alloc(size_t size) {  // arraylib.c:55-60 (host memory)
+    AL_ENTER;
+    if (size == 0) return set_error("ValueError: non-positive size in malloc."), nullptr;
+    void* p = malloc(size);
+    if (!p) set_error("MemoryError: failed to allocate memory.");
+    return p;
+}
+
+Data* data_empty(size_t size) {  // arraylib.c:129-137, with `mem` in device memory
+    AL_ENTER;
+    if (!ensure_init()) return nullptr;
+    if (size == 0) return set_error("ValueError: non-postive size in data_empty."), nullptr;
+    float* mem = (float*)device_alloc(size * sizeof(float));
+    if (!mem) return nullptr;
+    Data* d = (Data*)malloc(sizeof(Data));
+    d->mem = mem;
+    d->size = size;
+    d->refs = 1;
+    g_rt.bytes_in_use += size * sizeof(float);
+    return d;
+}
+
+Layout* layout_alloc(size_t ndim) {  // arraylib.c:143-149
+    AL_ENTER;
+    if (ndim == 0) return set_error("ValueError: non-positive ndim"), nullptr;
+    Layout* lay = (Layout*)malloc(sizeof(Layout));
+    lay->ndim = ndim;
+    lay->shape = (size_t*)calloc(ndim, sizeof(size_t));
+    lay->stride = (size_t*)calloc(ndim, sizeof(size_t));
+    return lay;
+}
+
+Layout* layout_copy(Layout* dst, const Layout* src) {  // arraylib.c:151-156 (dst must hold src->ndim entries)
+    AL_ENTER;
+    if (!dst || !src) return set_error("TypeError: layout_copy on NULL"), nullptr;
+    dst->ndim = src->ndim;
+    memcpy(dst->shape, src->shape, sizeof(size_t) * src->ndim);
+    memcpy(dst->stride, src->stride, sizeof(size_t) * src->ndim);
+    return dst;
+}
+
+void layout_free(Layout* lay) { free_layout(lay); }  // arraylib.c:158-162
+
+// arraylib.c:180-206: right-aligned broadcast of n layouts to a common rank; stride 0 on broadcast axes.
+Layout** layout_broadcast(const Layout** lays, size_t nlay) {
+    AL_ENTER;
+    if (!lays || nlay == 0) return set_error("TypeError: layout_broadcast on NULL"), nullptr;
+    size_t nd = 0;
+    for (size_t j = 0; j < nlay; j++) nd = lays[j]->ndim > nd ? lays[j]->ndim : nd;
+    Layout** out = (Layout**)malloc(sizeof(Layout*) * nlay);
+    for (size_t j = 0; j < nlay; j++) out[j] = layout_alloc(nd);
+    for (size_t k = 0; k < nd; k++) {
+        size_t e = 0;
+        for (size_t j = 0; j < nlay; j++) {
+            const size_t ej = k < lays[j]->ndim ? lays[j]->shape[lays[j]->ndim - 1 - k] : 1;
+            e = ej > e ? ej : e;
+        }
+        for (size_t j = 0; j < nlay; j++) {
+            const bool present = k < lays[j]->ndim && lays[j]->shape[lays[j]->ndim - 1 - k] == e;
+            out[j]->shape[nd - 1 - k] = e;
+            out[j]->stride[nd - 1 - k] = present ? lays[j]->stride[lays[j]->ndim - 1 - k] : 0;
+        }
+    }
+    return out;
+}
+
+// arraylib.c:491-501, 569-589 take a C function pointer: a host callback cannot run on the device.
+NDArray* array_scalar_op(binop, const NDArray*, f32) {
+    AL_ENTER;
+    set_error("NotImplementedError: host callbacks cannot run on the device; use array_scalar_op_named with an al_binop entry");
+    return nullptr;
+}
+NDArray* array_array_op(binop, const NDArray*, const NDArray*) {
+    AL_ENTER;
+    set_error("NotImplementedError: host callbacks cannot run on the device; use array_array_op_named with an al_binop entry");
+    return nullptr;
+}
+
 // ---- storage -------------------------------------------------------------------------------------
 NDArray* array_empty(const size_t* shape, size_t ndim) {
     AL_ENTER;

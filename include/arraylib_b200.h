@@ -86,6 +86,18 @@ void* al_host_alloc(size_t bytes);   /* pinned host memory for staging */
 int al_host_free(void* p);
 int al_set_tuning(const char* key, long value); /* kernel selection overrides, see DESIGN.md */
 
+/* ---- low-level helpers of the reference header (not used by its Python; present so its cdef binds) ---- */
+typedef f32 (*binop)(f32, f32);
+typedef f32 (*uniop)(f32);
+void* alloc(size_t size);                                           /* arraylib.c:55-60 (host memory) */
+Data* data_empty(size_t size);                                      /* arraylib.c:129-137; mem is device memory */
+Layout* layout_alloc(size_t ndim);                                  /* arraylib.c:143-149 */
+Layout* layout_copy(Layout* dst, const Layout* src);                /* arraylib.c:151-156 */
+void layout_free(Layout* lay);                                      /* arraylib.c:158-162 */
+Layout** layout_broadcast(const Layout** lays, size_t nlay);        /* arraylib.c:180-206 */
+NDArray* array_scalar_op(binop fn, const NDArray* src, f32 rhs);    /* arraylib.c:491-501: always fails (NotImplementedError) */
+NDArray* array_array_op(binop fn, const NDArray* lhs, const NDArray* rhs); /* arraylib.c:569-589: always fails (NotImplementedError) */
+
 /* ---- storage (arraylib.h "ARRAY CREATION AND DESTRUCTION"; arraylib.c:212-231) ------------ */
 NDArray* array_empty(const size_t* shape, size_t ndim);             /* arraylib.c:212-221 */
 void array_free(NDArray* array);                                    /* arraylib.c:223-231 */
@@ -183,8 +195,6 @@ typedef struct {
 NDArray* array_tape_eval_f64(const NDArray* const* inputs, size_t n_inputs, const al_tape_insn* tape, size_t n_insn, size_t result);
 
 /* ---- unary ufunc table (arraylib.c:638-665) ----------------------------------------------- */
-typedef f32 (*binop)(f32, f32);
-typedef f32 (*uniop)(f32);
 NDArray* array_op(uniop fn, const NDArray* src);       /* arraylib.c:638-645: always fails (NotImplementedError) */
 NDArray* array_op_named(int ufunc, const NDArray* src);
 NDArray* array_neg(const NDArray* src);

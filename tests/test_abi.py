@@ -73,3 +73,31 @@ def test_product_never_imports_the_oracle():
                     if needle in text:
                         bad.append((os.path.join(dirpath, f), needle))
     assert not bad, bad
+
+
+def test_reference_cffi_cdef_binds_completely():
+    """The strongest form of the drop-in claim that can be checked without a GPU: take the REFERENCE's own
+    header text (the part its core.py feeds to ffi.cdef, core.py:19-22), dlopen OUR library with it and
+    resolve every function it declares. Only runs where /root/reference exists (the build container)."""
+    import pytest
+    header = "/root/reference/arraylib/src/arraylib.h"
+    if not os.path.exists(header):
+        pytest.skip("reference sources not present on this machine")
+    cffi = pytest.importorskip("cffi")
+    from arraylib_b200._lib import LIB_PATH
+    ffi = cffi.FFI()
+    lines = open(header).read().splitlines()
+    text = "\n".join(lines[lines.index("// START"):lines.index("// END")])
+    ffi.cdef(text)
+    lib = ffi.dlopen(LIB_PATH)
+    names = sorted(set(re.findall(r"\b([a-z_0-9]+)\s*\(", re.sub(r"/\*.*?\*/", "", text, flags=re.S))))
+    names = [n for n in names if n not in ("f32", "clamp")]  # clamp is declared but never defined by the reference
+    assert len(names) >= 85
+    missing = []
+    for n in names:
+        try:
+            getattr(lib, n)
+        except AttributeError:
+            missing.append(n)
+    assert not missing, missing
+    assert (ffi.sizeof("NDArray"), ffi.sizeof("Data"), ffi.sizeof("Layout")) == (32, 24, 24)
