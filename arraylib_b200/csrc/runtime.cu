@@ -259,6 +259,20 @@ int al_init(int device) {
     if (!cuda_ok(cudaEventCreate(&g_rt.ev_start), "cudaEventCreate")) return -1;
     if (!cuda_ok(cudaEventCreate(&g_rt.ev_stop), "cudaEventCreate")) return -1;
     g_rt.device = device;
+    // ARRAYLIB_TUNING="key=value,key=value": the al_set_tuning knobs from the environment
+    if (const char* env = getenv("ARRAYLIB_TUNING")) {
+        std::string spec(env);
+        size_t pos = 0;
+        while (pos < spec.size()) {
+            size_t end = spec.find(',', pos);
+            if (end == std::string::npos) end = spec.size();
+            const std::string item = spec.substr(pos, end - pos);
+            const size_t eq = item.find('=');
+            if (eq != std::string::npos && al_set_tuning(item.substr(0, eq).c_str(), atol(item.c_str() + eq + 1)) != 0)
+                fprintf(stderr, "arraylib_b200: ignoring ARRAYLIB_TUNING entry '%s'\n", item.c_str());
+            pos = end + 1;
+        }
+    }
     clear_error();
     return 0;
 }

@@ -133,6 +133,21 @@ def bench_reduce():
     tune(reduce_splits=0)
 
 
+def bench_views():
+    """Elementwise ops on views that defeat the 128-bit path."""
+    n = 1 << 28
+    a, b = rnd((n + 8,), 1), rnd((n + 8,), 2)
+    timed(lambda: a[0:n] + b[0:n], 12 * n, "a[0:n] + b[0:n] (aligned slices)")
+    timed(lambda: a[1:n + 1] + b[1:n + 1], 12 * n, "a[1:n+1] + b[1:n+1] (both misaligned by 4 B)")
+    timed(lambda: a[1:n + 1] + b[0:n], 12 * n, "a[1:n+1] + b[0:n] (one misaligned)")
+    timed(lambda: a[0:n:2] + b[0:n:2], 12 * (n // 2), "a[::2] + b[::2] (inner stride 2)")
+    timed(lambda: al.copy(a[3:n + 3], deep=True), 8 * n, "deep copy of a[3:n+3]")
+    m = 16384
+    X = rnd((m, m + 4), 3)
+    timed(lambda: X[0:m, 1:m + 1] + 1.0, 8 * m * m, "X[:, 1:m+1] + 1.0 (rows misaligned, pitch m+4)")
+    timed(lambda: X[0:m, 0:m] + 1.0, 8 * m * m, "X[:, 0:m] + 1.0 (rows aligned, pitch m+4)")
+
+
 def bench_ops():
     n = 1 << 28
     a, b = rnd((n,), 1), rnd((n,), 2)
