@@ -406,7 +406,23 @@ struct ChainPlan {
 };
 
 template <int VEC, int NIN>
-static bool launch_chain_one(const ChainPlan& plan, const Folded& fo, const float* const* in, float* out, uint64_t) {
+static bool launch_chain_one(const ChainPlan& plan, const Folded& fo_in, const float* const* in, float* out, uint64_t) {
+    // A flat contiguous stream has no outer axis to block over: view [n] as [rows, n/rows] so that the
+    // row-blocked kernel (one op decode per 8 vectors) applies; lanes stay coalesced along n/rows.
+    Folded fo = fo_in;
+    if (VEC == 4 && fo.ndim == 1 && !plan.full && rt().chain_block >= 2 && NIN <= 2 &&
+        fo.extent[0] % (4 * kChainRows) == 0 && fo.extent[0] >= (1u << 16)) {
+        bool ok = true;
+        for (int i = 0; i < NIN; i++) ok = ok && (fo.in_stride[i][0] == 1);
+        if (ok) {
+            const uint64_t cols = fo.extent[0] / kChainRows;
+            fo.ndim = 2;
+            fo.extent[0] = cols;
+            fo.extent[1] = kChainRows;
+            fo.out_stride[1] = (int64_t)cols;
+            for (int i = 0; i < NIN; i++) fo.in_stride[i][1] = (int64_t)cols;
+        }
+    }
     ChainArgs<NIN> ca;
     memset(&ca, 0, sizeof ca);
     NdArgs<NIN>& a = ca.nd;

@@ -128,3 +128,18 @@ def test_apply_lambdas_against_reference_golden(al):
     assert_bit_equal(al.to_numpy(X.apply(lambda v: 2 * v * v + 1)), gold["apply_poly"], "poly")
     assert_bit_equal(al.to_numpy(X.apply(lambda v: 1 / (1 + v * v) - v / 3)), gold["apply_rational"], "rational")
     assert_bit_equal(al.to_numpy(X.apply(lambda v: abs(v - 2.5) * -1.0 + (v > 1.0) * v)), gold["apply_mixed"], "mixed")
+
+
+def test_flat_contiguous_chains_take_the_row_blocked_kernel(al, rng):
+    from arraylib_b200._lib import lib
+    n = 1 << 17
+    a, b = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    A, B = al.from_numpy(a), al.from_numpy(b)
+    got = ((al.lazy(A) + B) * 0.5 - 1.0).eval()
+    assert lib.al_last_kernel() == b"ew_chain_vec4_rows8"
+    assert_bit_equal(al.to_numpy(got), al.to_numpy((A + B) * 0.5 - 1.0), "flat binary chain")
+    got = (al.lazy(A).abs().sqrt() * 2.0).eval()
+    assert lib.al_last_kernel() == b"ew_chain_vec4_rows8"
+    assert_bit_equal(al.to_numpy(got), al.to_numpy(al.sqrt(al.abs(A)) * 2.0), "flat unary chain")
+    got = (al.lazy(A.reshape((512, 256))) * B.reshape((512, 256)) - A.reshape((512, 256))).eval()  # three arrays: generic kernel
+    assert_bit_equal(al.to_numpy(got), (a * b - a).reshape(512, 256), "three-array flat chain")

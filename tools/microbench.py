@@ -133,6 +133,19 @@ def bench_reduce():
     tune(reduce_splits=0)
 
 
+def bench_fused():
+    n = 1 << 28
+    a, b, c = rnd((n,), 1), rnd((n,), 2), rnd((n,), 3)
+    timed(lambda: a * b + c, 12 * n + 12 * n, "eager a*b+c 2^28 (two passes, 24 B/elem algorithmic)")
+    timed(lambda: (al.lazy(a) * b + c).eval(), 16 * n, "fused a*b+c 2^28 (16 B/elem)")
+    timed(lambda: ((al.lazy(a) + b) * 0.5 - 1.0).eval(), 12 * n, "fused (a+b)*0.5-1 2^28 (12 B/elem)")
+    timed(lambda: (al.lazy(a).abs().sqrt() * 2.0).eval(), 8 * n, "fused sqrt(|a|)*2 2^28 (8 B/elem)")
+    timed(lambda: al.apply(lambda v: 2 * v * v + 1, a), 8 * n, "apply(lambda v: 2*v*v+1) FP64 tape 2^28")
+    timed(lambda: al.apply(lambda v: 1 / (1 + v * v) - v / 3, a), 8 * n, "apply(rational lambda) FP64 tape 2^28")
+    A, B, cc = rnd((1024, 1, 4096), 1), rnd((1, 1024, 4096), 2), rnd((4096,), 3)
+    timed(lambda: (al.lazy(A) + B + cc + 1.0).eval(), 4 * (1 << 32), "fused C3 chain A+B+c+1.0 (README-style, 17.2 GB)")
+
+
 def bench_views():
     """Elementwise ops on views that defeat the 128-bit path."""
     n = 1 << 28
