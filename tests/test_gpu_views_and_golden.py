@@ -218,3 +218,38 @@ def test_arange_random_parameters_through_the_c_abi(al, orc):
         assert_bit_equal(al.to_numpy(got), want, f"arange({start}, {end}, {step})")
     for start, end, n in [(0, 10, 5), (1, 100, 10), (3, 7, 11), (0, 1, 1000), (5, 6, 3)]:
         assert_bit_equal(al.to_numpy(al.linspace(start, end, n)), orc.linspace(start, end, n), f"linspace {start} {end} {n}")
+
+
+def test_concurrent_python_threads(al, rng):
+    """ctypes drops the GIL around every call; the library serialises on its own lock and recycles
+    device blocks in stream order, so independent threads can interleave ops and frees freely."""
+    import threading
+    data = [rng.standard_normal((257, 130)).astype(np.float32) for _ in range(6)]
+    results, errors = {}, []
+
+    def work(tid):
+        try:
+            x = data[tid]
+            X = al.from_numpy(x)
+            acc = X
+            for k in range(25):
+                acc = (acc + X) * 0.5 - float(k % 3)
+                if k % 5 == 0:
+                    tmp = al.copy(acc.transpose((1, 0)), deep=True)  # allocate / free churn
+                    del tmp
+            results[tid] = (al.to_numpy(acc), al.to_numpy(al.reduce_max(X, dims=(0,))))
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(data))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for tid, x in enumerate(data):
+        acc = x.copy()
+        for k in range(25):
+            acc = (acc + x) * np.float32(0.5) - np.float32(k % 3)
+        assert_bit_equal(results[tid][0], acc, f"thread {tid}")
+        assert_bit_equal(results[tid][1], x.max(axis=0, keepdims=True), f"thread {tid} max")
