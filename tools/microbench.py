@@ -146,6 +146,30 @@ def bench_fused():
     timed(lambda: (al.lazy(A) + B + cc + 1.0).eval(), 4 * (1 << 32), "fused C3 chain A+B+c+1.0 (README-style, 17.2 GB)")
 
 
+def bench_pcie():
+    import time
+    n = 1 << 30
+    buf = al.host_buffer((n,))
+    buf[:] = 1.0
+    for label, fn in (("H2D 4 GiB pinned (blocking)", lambda: al.from_numpy(buf)),):
+        fn()
+        t0 = time.perf_counter(); x = fn(); al.synchronize(); dt = time.perf_counter() - t0
+        print(f"{label:40s} {dt*1e3:8.1f} ms  {4*n/dt/1e9:6.1f} GB/s", flush=True)
+    X = al.from_numpy(buf)
+    t0 = time.perf_counter(); al.to_numpy(X, out=buf); dt = time.perf_counter() - t0
+    print(f"{'D2H 4 GiB pinned (blocking)':40s} {dt*1e3:8.1f} ms  {4*n/dt/1e9:6.1f} GB/s", flush=True)
+    buf2 = al.host_buffer((n,))
+    t0 = time.perf_counter()
+    Y = al.from_numpy(buf2, blocking=False); al.to_numpy(X, out=buf, blocking=False); al.synchronize()
+    dt = time.perf_counter() - t0
+    print(f"{'H2D + D2H 4 GiB each, concurrent':40s} {dt*1e3:8.1f} ms  {8*n/dt/1e9:6.1f} GB/s total", flush=True)
+    pageable = np.ones(n, np.float32)
+    t0 = time.perf_counter(); Z = al.from_numpy(pageable); al.synchronize(); dt = time.perf_counter() - t0
+    print(f"{'H2D 4 GiB pageable':40s} {dt*1e3:8.1f} ms  {4*n/dt/1e9:6.1f} GB/s", flush=True)
+    t0 = time.perf_counter(); h = al.to_numpy(Z); dt = time.perf_counter() - t0
+    print(f"{'D2H 4 GiB pageable (fresh np.empty)':40s} {dt*1e3:8.1f} ms  {4*n/dt/1e9:6.1f} GB/s", flush=True)
+
+
 def bench_views():
     """Elementwise ops on views that defeat the 128-bit path."""
     n = 1 << 28
