@@ -43,6 +43,7 @@ struct Runtime {
     long tile64 = 1;           // 0: use the 32x32 scalar transpose tile even when the float4 one applies
     long tile_tq = 64;         // q extent of the 128-bit transpose tile: 32, 64 or 128 (p extent = 4096 / tq)
     long chain_block = 2;      // fused chains: 0 one vector per thread, 1 generic 4-row blocks, 2 also the specialised 8-row kernel
+    long stream_tma = 0;       // 1: contiguous add/mul through the cp.async.bulk + mbarrier pipeline (experiment)
     long interleave = 1;       // 0: short-axis transposes always use the rectangular tile kernel
     long outer_tile = 1;       // 0: do not use the register-tiled outer-broadcast kernel
 };

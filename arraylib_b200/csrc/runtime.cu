@@ -378,6 +378,7 @@ int al_set_tuning(const char* key, long value) {
     else if (k == "tile64") g_rt.tile64 = value;
     else if (k == "tile_tq") g_rt.tile_tq = value;
     else if (k == "interleave") g_rt.interleave = value;
+    else if (k == "stream_tma") g_rt.stream_tma = value;
     else if (k == "chain_block") g_rt.chain_block = value;
     else if (k == "outer_tile") g_rt.outer_tile = value;
     else {

@@ -207,6 +207,23 @@ def test_short_axis_transposes(al, rng, shape, perm):
         assert seen & {b"ew_interleave", b"ew_deinterleave"}, seen
 
 
+@pytest.mark.parametrize("n", [4096 * 148, 4096 * 148 * 3 + 4096 + 8, (1 << 23) + 4, 1 << 24])
+def test_bulk_async_stream_experiment(al, rng, n):
+    """The cp.async.bulk + mbarrier streaming kernel (off by default) computes the same bits."""
+    from arraylib_b200._lib import lib
+    a, b = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    A, B = al.from_numpy(a), al.from_numpy(b)
+    lib.al_set_tuning(b"stream_tma", 1)
+    try:
+        s = al.to_numpy(A + B)
+        assert lib.al_last_kernel() == b"ew_stream_tma"
+        m = al.to_numpy(A * B)
+    finally:
+        lib.al_set_tuning(b"stream_tma", 0)
+    assert_bit_equal(s, a + b, "tma add")
+    assert_bit_equal(m, a * b, "tma mul")
+
+
 def test_general_fallback_equals_fast_paths(al, rng):
     """force_general=1 routes everything through the scalar gather kernel; results must not move."""
     from arraylib_b200._lib import lib

@@ -58,6 +58,9 @@ def bench_ew():
                 tune(ew_unroll=unroll, load_policy=pol, stream_store_min_bytes=ss)
                 timed(lambda: a + b, 12 * n, f"a+b 2^28 unroll={unroll} load_policy={pol} stream_store={'on' if ss == 0 else 'off'}", reps=5)
     tune(ew_unroll=4, load_policy=0, stream_store_min_bytes=64 << 20)
+    tune(stream_tma=1)
+    timed(lambda: a + b, 12 * n, "a+b 2^28 cp.async.bulk + mbarrier pipeline (experiment)")
+    tune(stream_tma=0)
     timed(lambda: a + 1.0, 8 * n, "a+1.0 2^28")
     timed(lambda: al.copy(a, deep=True), 8 * n, "deep copy 2^28 (contiguous)")
 
@@ -168,6 +171,24 @@ def bench_pcie():
     print(f"{'H2D 4 GiB pageable':40s} {dt*1e3:8.1f} ms  {4*n/dt/1e9:6.1f} GB/s", flush=True)
     t0 = time.perf_counter(); h = al.to_numpy(Z); dt = time.perf_counter() - t0
     print(f"{'D2H 4 GiB pageable (fresh np.empty)':40s} {dt*1e3:8.1f} ms  {4*n/dt/1e9:6.1f} GB/s", flush=True)
+
+
+def bench_latency():
+    """Host-side cost per op on tiny arrays (the C1 / README regime)."""
+    import time
+    a, b = al.ones((3, 6)), al.ones((6,))
+    for label, fn in (("a + b (tiny, broadcast)", lambda: a + b), ("a + 1.0 (tiny)", lambda: a + 1.0),
+                      ("a.reshape", lambda: a.reshape((6, 3))), ("a.reduce_sum(dims=(1,))", lambda: a.reduce_sum(dims=(1,))),
+                      ("a.shape property", lambda: a.shape)):
+        for _ in range(200):
+            fn()
+        al.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5000):
+            r = fn()
+        al.synchronize()
+        dt = (time.perf_counter() - t0) / 5000
+        print(f"{label:34s} {dt*1e6:8.2f} us per call", flush=True)
 
 
 def bench_views():
