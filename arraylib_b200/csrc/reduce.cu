@@ -423,33 +423,37 @@ reduce_window_fixed_kernel(const float* __restrict__ x, float* __restrict__ out,
     }
 }
 
-// w = 64 variant (config C5a): like the kernel above, but a block is split between two adjacent lanes.
-// Each lane reads only its 32 elements (one shared read per element instead of two), builds the
-// prefix and suffix scans of its half in registers, swaps half totals with its partner through one
-// shuffle and adds the partner's total to the scan that crosses the middle of the block. That is 8
-// LSU operations per output instead of 9, on the pipe that bounds this kernel. Blocks are laid out
-// with a pitch of 66 floats and a one-float gap between the halves, so the 16 blocks x 2 halves a
-// warp touches fall on 32 different banks.
-template <int OP>
+// Half-block variant (default for w = 8/16/32/64; config C5a uses w = 64): like the kernel above, but a
+// block is split between two adjacent lanes. Each lane reads only its w/2 elements (one shared read per
+// element instead of two), builds the prefix and suffix scans of its half in registers, swaps half
+// totals with its partner through one shuffle and folds the partner's total into the scan that crosses
+// the middle of the block. That is 8 LSU operations per output instead of 9, on the pipe that bounds
+// this kernel. Blocks are laid out with a pitch of w+2 floats and a one-float gap between the halves;
+// consecutive lanes own consecutive half blocks, so a warp's 32 half blocks fall on 32 different banks
+// for every w (the whole-block kernel strides lanes by 64/w blocks and conflicts for w < 64).
+template <int OP, int W>
 __global__ void __launch_bounds__(kWinFixedThreads, 4)
-reduce_window64_kernel(const float* __restrict__ x, float* __restrict__ out, uint32_t nout, uint32_t n_tiles,
-                       uint32_t tiles_per_row, long long row_stride, float init, int init_is_identity) {
+reduce_window_half_kernel(const float* __restrict__ x, float* __restrict__ out, uint32_t nout, uint32_t n_tiles,
+                          uint32_t tiles_per_row, long long row_stride, float init, int init_is_identity) {
     extern __shared__ float wsm[];
-    constexpr int W = 64, H = 32, T = kWinFixedThreads, SPAN = kWinFixedThreads * kWinLoads;
-    constexpr int PITCH = 66, NBLK = SPAN / W, TILE = SPAN - W;
-    static_assert(T == 2 * NBLK, "one lane per half block");
+    constexpr int H = W / 2, T = kWinFixedThreads, SPAN = kWinFixedThreads * kWinLoads;
+    constexpr int PITCH = W + 2, NBLK = SPAN / W, TILE = SPAN - W;
+    constexpr int UPT = 2 * NBLK / T;  // half blocks per lane: UPT * H == kWinLoads
+    constexpr int SHIFT = W == 64 ? 6 : W == 32 ? 5 : W == 16 ? 4 : 3;
+    constexpr int BLK_PER_ROUND = T / W;
+    static_assert(UPT * H == kWinLoads && UPT >= 1, "a lane holds kWinLoads elements");
     float* P = wsm;
     float* S = wsm + NBLK * PITCH;
     const size_t n_in = (size_t)nout + W - 1;
     const int tid = threadIdx.x;
-    // element e = u*T + tid of a tile: block 2u + tid/64, offset kk = tid%64, stored at kk + kk/32
+    // element e = u*T + tid of a tile: block u*T/W + tid/W, offset kk = tid%W, stored at kk + (kk >= H)
     const int kk = tid & (W - 1);
-    const int slot = (tid >> 6) * PITCH + kk + (kk >> 5);
+    const int slot = (tid >> SHIFT) * PITCH + kk + (kk >= H ? 1 : 0);
     float* const stage = P + slot;
     const float* const s_lane = S + slot;
-    const float* const p_lane = P + ((tid >> 6) + 1) * PITCH + (kk - 1) + ((kk - 1) >> 5);  // P[b+1][kk-1] (kk >= 1)
+    const float* const p_lane = P + ((tid >> SHIFT) + 1) * PITCH + (kk - 1) + (kk - 1 >= H ? 1 : 0);  // P[b+1][kk-1], kk >= 1
     const int half = tid & 1;
-    const int scan_base = (tid >> 1) * PITCH + half * (H + 1);
+    const int scan_base = (tid >> 1) * PITCH + half * (H + 1);  // unit m adds m * (T/2) blocks
     const bool has_head = kk != 0;
     const bool ident = init_is_identity != 0;
 
@@ -470,28 +474,34 @@ reduce_window64_kernel(const float* __restrict__ x, float* __restrict__ out, uin
     if (tile < n_tiles) fetch(tile);
     for (; tile < n_tiles; tile += gridDim.x) {
 #pragma unroll
-        for (int u = 0; u < kWinLoads; u++) stage[u * 2 * PITCH] = v[u];
+        for (int u = 0; u < kWinLoads; u++) stage[u * BLK_PER_ROUND * PITCH] = v[u];
         __syncthreads();
         if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);
-        float xr[H];
+        float xr[UPT][H];
 #pragma unroll
-        for (int k = 0; k < H; k++) xr[k] = P[scan_base + k];
+        for (int m = 0; m < UPT; m++)
+#pragma unroll
+            for (int k = 0; k < H; k++) xr[m][k] = P[scan_base + m * (T / 2) * PITCH + k];
         __syncthreads();  // every half block is in registers before P is overwritten in place
-        float lp[H];
-        lp[0] = xr[0];
 #pragma unroll
-        for (int k = 1; k < H; k++) lp[k] = racc<OP>(lp[k - 1], xr[k]);
-        const float other = __shfl_xor_sync(0xffffffffu, lp[H - 1], 1);  // partner's half total
-        const float before = half ? other : rident<OP>();  // what precedes this half inside the block
-        const float after = half ? rident<OP>() : other;   // what follows it
+        for (int m = 0; m < UPT; m++) {
+            const int base = scan_base + m * (T / 2) * PITCH;
+            float lp[H];
+            lp[0] = xr[m][0];
 #pragma unroll
-        for (int k = 0; k < H; k++) P[scan_base + k] = racc<OP>(before, lp[k]);
-        float run = xr[H - 1];
-        S[scan_base + H - 1] = racc<OP>(run, after);
+            for (int k = 1; k < H; k++) lp[k] = racc<OP>(lp[k - 1], xr[m][k]);
+            const float other = __shfl_xor_sync(0xffffffffu, lp[H - 1], 1);  // partner's half total
+            const float before = half ? other : rident<OP>();  // what precedes this half inside the block
+            const float after = half ? rident<OP>() : other;   // what follows it
 #pragma unroll
-        for (int k = H - 2; k >= 0; k--) {
-            run = racc<OP>(xr[k], run);
-            S[scan_base + k] = racc<OP>(run, after);
+            for (int k = 0; k < H; k++) P[base + k] = racc<OP>(before, lp[k]);
+            float run = xr[m][H - 1];
+            S[base + H - 1] = racc<OP>(run, after);
+#pragma unroll
+            for (int k = H - 2; k >= 0; k--) {
+                run = racc<OP>(xr[m][k], run);
+                S[base + k] = racc<OP>(run, after);
+            }
         }
         __syncthreads();
         const uint32_t row = tile / tiles_per_row;
@@ -501,8 +511,8 @@ reduce_window64_kernel(const float* __restrict__ x, float* __restrict__ out, uin
 #pragma unroll
             for (int u = 0; u < kWinLoads; u++) {
                 if (u * T + tid < TILE) {
-                    float r = s_lane[u * 2 * PITCH];
-                    if (has_head) r = racc<OP>(r, p_lane[u * 2 * PITCH]);
+                    float r = s_lane[u * BLK_PER_ROUND * PITCH];
+                    if (has_head) r = racc<OP>(r, p_lane[u * BLK_PER_ROUND * PITCH]);
                     __stcs(dst + u * T, rfinal_fast<OP>(init, r, ident));
                 }
             }
@@ -510,8 +520,8 @@ reduce_window64_kernel(const float* __restrict__ x, float* __restrict__ out, uin
 #pragma unroll
             for (int u = 0; u < kWinLoads; u++) {
                 if (u * T + tid < TILE && i0 + u * T + tid < nout) {
-                    float r = s_lane[u * 2 * PITCH];
-                    if (has_head) r = racc<OP>(r, p_lane[u * 2 * PITCH]);
+                    float r = s_lane[u * BLK_PER_ROUND * PITCH];
+                    if (has_head) r = racc<OP>(r, p_lane[u * BLK_PER_ROUND * PITCH]);
                     __stcs(dst + u * T, rfinal_fast<OP>(init, r, ident));
                 }
             }
@@ -584,13 +594,13 @@ static bool launch_window_fixed(const float* src, float* out, uint32_t nout, uin
     const int init_is_identity = memcmp(&init, &ident_tab[OP], sizeof(float)) == 0;
     constexpr int kWinSpan = kWinFixedThreads * kWinLoads;
     constexpr int TILE = kWinSpan - W;
-    const bool split_halves = W == 64 && !rt().window_whole_blocks;
-    const size_t smem = 2ull * (kWinSpan / W) * (split_halves ? 66 : W + 1) * sizeof(float);
+    const bool split_halves = !rt().window_whole_blocks;
+    const size_t smem = 2ull * (kWinSpan / W) * (split_halves ? W + 2 : W + 1) * sizeof(float);
     static bool configured = false;
     if (!configured) {
-        if (!cuda_ok(cudaFuncSetAttribute(reduce_window_fixed_kernel<OP, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024),
+        if (!cuda_ok(cudaFuncSetAttribute(reduce_window_fixed_kernel<OP, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 8192),
                      "cudaFuncSetAttribute") ||
-            !cuda_ok(cudaFuncSetAttribute(reduce_window64_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024),
+            !cuda_ok(cudaFuncSetAttribute(reduce_window_half_kernel<OP, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 8192),
                      "cudaFuncSetAttribute"))
             return false;
         configured = true;
@@ -603,7 +613,7 @@ static bool launch_window_fixed(const float* src, float* out, uint32_t nout, uin
     unsigned blocks = (unsigned)(kNumSMs * per_sm);
     if (blocks > n_tiles) blocks = n_tiles;
     if (split_halves)
-        reduce_window64_kernel<OP><<<blocks, kWinFixedThreads, smem, rt().stream>>>(src, out, nout, n_tiles, tiles_per_row, row_stride, init, init_is_identity);
+        reduce_window_half_kernel<OP, W><<<blocks, kWinFixedThreads, smem, rt().stream>>>(src, out, nout, n_tiles, tiles_per_row, row_stride, init, init_is_identity);
     else
         reduce_window_fixed_kernel<OP, W><<<blocks, kWinFixedThreads, smem, rt().stream>>>(src, out, nout, n_tiles, tiles_per_row, row_stride, init, init_is_identity);
     note_launch("reduce_window");

@@ -161,9 +161,10 @@ def test_window_kernel_matches_generic_path(al, rng):
     assert_bit_equal(fast, slow, "window vs generic")
 
 
-def test_window_half_block_and_whole_block_kernels_agree(al, orc, rng):
+@pytest.mark.parametrize("w", [8, 16, 32, 64])
+def test_window_half_block_and_whole_block_kernels_agree(al, orc, rng, w):
     from arraylib_b200._lib import lib
-    n, w = 300000, 64
+    n = 300000
     base = int_data(rng, (n,))
     base[1000:1100] = np.nan  # a stretch of all-NaN windows: max/min must give the identity like the reference
     V = al.from_numpy(base).as_strided(shape=(n - w + 1, w), stride=(1, 1))
