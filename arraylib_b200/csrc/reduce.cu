@@ -451,7 +451,10 @@ reduce_window_half_kernel(const float* __restrict__ x, float* __restrict__ out, 
     const int slot = (tid >> SHIFT) * PITCH + kk + (kk >= H ? 1 : 0);
     float* const stage = P + slot;
     const float* const s_lane = S + slot;
-    const float* const p_lane = P + ((tid >> SHIFT) + 1) * PITCH + (kk - 1) + (kk - 1 >= H ? 1 : 0);  // P[b+1][kk-1], kk >= 1
+    // Prefix values are stored one logical slot to the right (P[b][k] sits where element k+1 would), so
+    // that the read of P[b+1][kk-1] uses the same lane->bank map as S[b][kk] (reading it in place would
+    // straddle the gap between the halves and collide on one bank in every second warp).
+    const float* const p_lane = P + slot + PITCH;  // P[b+1][kk-1], kk >= 1
     const int half = tid & 1;
     const int scan_base = (tid >> 1) * PITCH + half * (H + 1);  // unit m adds m * (T/2) blocks
     const bool has_head = kk != 0;
@@ -493,8 +496,9 @@ reduce_window_half_kernel(const float* __restrict__ x, float* __restrict__ out, 
             const float other = __shfl_xor_sync(0xffffffffu, lp[H - 1], 1);  // partner's half total
             const float before = half ? other : rident<OP>();  // what precedes this half inside the block
             const float after = half ? rident<OP>() : other;   // what follows it
+            float* const pw = P + (base - half * (H + 1)) + (half ? H + 2 : 1);  // shifted home of this half's prefixes
 #pragma unroll
-            for (int k = 0; k < H; k++) P[base + k] = racc<OP>(before, lp[k]);
+            for (int k = 0; k < H; k++) pw[k + ((!half && k == H - 1) ? 1 : 0)] = racc<OP>(before, lp[k]);
             float run = xr[m][H - 1];
             S[base + H - 1] = racc<OP>(run, after);
 #pragma unroll
