@@ -37,6 +37,7 @@ struct Runtime {
     long load_policy = 0;      // streaming loads: 0 ld.global.cs, 1 ld.global.nc, 2 nc+L1::no_allocate
     long force_general = 0;    // 1: disable the vector / tile fast paths (tests the fallback)
     long reduce_splits = 0;    // 0 = auto
+    long reduce_sequential = 0;  // 1: one thread per output, the reference's summation order (bit-exact, slow)
     long disable_window = 0;
     long window_whole_blocks = 0;  // 1: fixed-w windows use the whole-block scan kernel instead of the half-block one
     long window_ctas_per_sm = 0;  // 0 = default (32 CTAs per SM, 4 of them resident)

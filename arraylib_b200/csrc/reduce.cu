@@ -270,6 +270,30 @@ __global__ void __launch_bounds__(256) reduce_inner_cta_kernel(const RedArgs a) 
     }
 }
 
+// ---- reduce_sequential: the reference's own summation order (verification mode) --------------------------
+// One thread per output walks its reduced elements in ascending logical order and accumulates exactly
+// like the serial reference build (arraylib.c:737-750): acc = init; acc = fn(acc, x) ...; out = fn(init, acc).
+// Slow by construction (no parallelism inside an output); selected with al_set_tuning("reduce_sequential", 1)
+// to show that the ONLY difference between reduce_sum here and in the reference is the order of the adds.
+template <int OP>
+__global__ void __launch_bounds__(256) reduce_sequential_kernel(const RedArgs a) {
+    const uint32_t o = blockIdx.x * 256u + threadIdx.x;
+    if (o >= a.nout) return;
+    const float* base = a.src + (a.nk ? kept_offset(a, o) : 0);
+    float acc = a.init;
+    for (uint32_t r = 0; r < a.nr_items; r++) {
+        const float x = base[red_offset(a, r)];
+        if constexpr (OP == AL_RMAX) acc = (acc >= x || x != x) ? acc : x;       // glibc fmax, left operand wins ties
+        else if constexpr (OP == AL_RMIN) acc = (acc <= x || x != x) ? acc : x;  // glibc fmin
+        else acc = racc<OP>(acc, x);
+    }
+    float r2;
+    if constexpr (OP == AL_RMAX) r2 = (a.init >= acc || acc != acc) ? a.init : acc;
+    else if constexpr (OP == AL_RMIN) r2 = (a.init <= acc || acc != acc) ? a.init : acc;
+    else r2 = racc<OP>(a.init, acc);
+    a.dst[o] = r2;
+}
+
 // ---- reduce_finish: out[o] = final(sum_s partial[s][o]) ------------------------------------------
 template <int OP>
 __global__ void __launch_bounds__(256)
@@ -670,6 +694,29 @@ static bool run_reduce(const float* src, float* out, const AxisList& K, const Ax
     a.nk = K.n;
     a.nr = R.n;
     const bool general = r.force_general;
+    if (r.reduce_sequential) {
+        for (int d = 0; d < K.n; d++) {
+            a.kext[d] = (uint32_t)K.extent[d];
+            a.kstride[d] = K.stride[d];
+            a.kdiv[d] = make_fastdiv(a.kext[d]);
+        }
+        for (int d = 0; d < R.n; d++) {
+            a.rext[d] = (uint32_t)R.extent[d];
+            a.rstride[d] = R.stride[d];
+            a.rdiv[d] = make_fastdiv(a.rext[d]);
+        }
+        if (R.n == 0) {
+            a.nr = 1;
+            a.rext[0] = 1;
+            a.rstride[0] = 0;
+            a.rdiv[0] = make_fastdiv(1);
+        }
+        a.nr_items = (uint32_t)rtot;
+        a.dst = out;
+        reduce_sequential_kernel<OP><<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(a);
+        note_launch("reduce_sequential");
+        return check_launch("reduce_sequential");
+    }
 
     // -- overlapping windows (C5a): kept stride == reduced stride == 1, optionally a batch of rows --
     const bool win_axes = R.n == 1 && R.stride[0] == 1 && (K.n == 1 || K.n == 2) && K.stride[0] == 1;

@@ -219,3 +219,33 @@ def test_reduce_with_callable_and_init(al, orc, rng):
     assert_bit_equal(al.to_numpy(got), orc.reduce("sum", x, (3,), init=2.0), "sum init 2")
     with pytest.raises(NotImplementedError):
         al.reduce(lambda a, b: a - b, X, dims=(0,))
+
+
+@pytest.mark.parametrize("shape", [(7,), (5, 64), (16, 33, 8), (4, 13, 3, 12), (2, 3, 4, 5, 6), (300, 9)])
+def test_sequential_mode_reproduces_the_reference_bit_for_bit(al, orc, ref, rng, shape):
+    """With reduce_sequential=1 every output is accumulated in the reference's own order, so even
+    float reduce_sum matches the serial reference bit for bit -- the tolerance of the fast kernels is
+    purely the order of the additions."""
+    from arraylib_b200._lib import lib
+    x = rng.standard_normal(shape).astype(np.float32) * np.float32(100)
+    x.reshape(-1)[::11] = np.float32(-0.0)
+    X = al.from_numpy(x)
+    views = [(X, x)]
+    if len(shape) > 1:
+        perm = tuple(reversed(range(len(shape))))
+        views.append((X.transpose(perm), np.transpose(x, perm)))
+    lib.al_set_tuning(b"reduce_sequential", 1)
+    try:
+        for V, v in views:
+            for dims in power_set(tuple(range(v.ndim))):
+                for op in ("sum", "max", "min"):
+                    got = getattr(al, f"reduce_{op}")(V, dims=dims)
+                    assert lib.al_last_kernel() == b"reduce_sequential"
+                    assert_bit_equal(al.to_numpy(got), orc.reduce(op, v, dims), f"{op} {shape} {dims}")
+            got = al.reduce(lambda a_, b_: a_ + b_, V, dims=(0,), init=1.5)
+            assert_bit_equal(al.to_numpy(got), orc.reduce("sum", v, (0,), init=1.5), "custom init")
+        if ref is not None:
+            want = ref.reduce("sum", ref.from_numpy(x), tuple(range(len(shape)))[:1]).numpy()
+            assert_bit_equal(al.to_numpy(al.reduce_sum(X, dims=tuple(range(len(shape)))[:1])), want, "vs compiled reference")
+    finally:
+        lib.al_set_tuning(b"reduce_sequential", 0)
