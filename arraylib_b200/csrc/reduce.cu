@@ -19,6 +19,8 @@
 //
 // Summation order differs from the reference (tree instead of sequential), so reduce_sum carries
 // the tolerance stated in DESIGN.md; max/min are order independent.
+#include <algorithm>
+
 #include "al_internal.h"
 #include "device_utils.cuh"
 
@@ -204,25 +206,45 @@ __global__ void __launch_bounds__(256) reduce_inner_kernel(const RedArgs a) {
     const uint32_t gt = (uint32_t)(((uint64_t)blockIdx.x * 256u + threadIdx.x) / TEAM);  // team id == output id (64-bit: nout*TEAM may pass 2^32)
     const uint32_t lane = threadIdx.x % TEAM;
     const bool live = gt < a.nout;
-    const uint32_t r0 = blockIdx.y * a.r_per_split;
-    const uint32_t r1 = min(r0 + a.r_per_split, a.nr_items);
     Acc<VEC> acc = acc_ident<OP, VEC>();
     if (live) {
         const float* base = a.src + (a.nk ? kept_offset(a, gt) : 0);
-        uint32_t r = r0 + lane;
-        for (; r + 3 * TEAM < r1; r += 4 * TEAM) {
-            Acc<VEC> x0 = ld_acc<VEC>(base + red_offset(a, r));
-            Acc<VEC> x1 = ld_acc<VEC>(base + red_offset(a, r + TEAM));
-            Acc<VEC> x2 = ld_acc<VEC>(base + red_offset(a, r + 2 * TEAM));
-            Acc<VEC> x3 = ld_acc<VEC>(base + red_offset(a, r + 3 * TEAM));
-            acc_into<OP, VEC>(x0, x1);
-            acc_into<OP, VEC>(x2, x3);
-            acc_into<OP, VEC>(x0, x2);
-            acc_into<OP, VEC>(acc, x0);
-        }
-        for (; r < r1; r += TEAM) {
-            Acc<VEC> x = ld_acc<VEC>(base + red_offset(a, r));
-            acc_into<OP, VEC>(acc, x);
+        // Lanes run along the innermost reduced axis; the outer reduced axes are walked by a plain loop
+        // whose offset is resolved once per row (not once per load). This kernel is never split
+        // (gridDim.y == 1), so the range is always the whole reduced space.
+        const uint32_t e0 = a.rext[0];
+        const uint32_t n_outer = a.nr_items / e0;
+        const long long s0 = a.rstride[0];
+        for (uint32_t ro = 0; ro < n_outer; ro++) {
+            long long obase = 0;
+            uint32_t rem = ro;
+            for (int d = 1; d < a.nr; d++) {
+                uint32_t idx;
+                if (d == a.nr - 1) {
+                    idx = rem;
+                } else {
+                    const uint32_t q = fdiv(rem, a.rdiv[d]);
+                    idx = rem - q * a.rext[d];
+                    rem = q;
+                }
+                obase += (long long)idx * a.rstride[d];
+            }
+            const float* row = base + obase;
+            uint32_t r = lane;
+            for (; r + 3 * TEAM < e0; r += 4 * TEAM) {
+                Acc<VEC> x0 = ld_acc<VEC>(row + (long long)r * s0);
+                Acc<VEC> x1 = ld_acc<VEC>(row + (long long)(r + TEAM) * s0);
+                Acc<VEC> x2 = ld_acc<VEC>(row + (long long)(r + 2 * TEAM) * s0);
+                Acc<VEC> x3 = ld_acc<VEC>(row + (long long)(r + 3 * TEAM) * s0);
+                acc_into<OP, VEC>(x0, x1);
+                acc_into<OP, VEC>(x2, x3);
+                acc_into<OP, VEC>(x0, x2);
+                acc_into<OP, VEC>(acc, x0);
+            }
+            for (; r < e0; r += TEAM) {
+                Acc<VEC> x = ld_acc<VEC>(row + (long long)r * s0);
+                acc_into<OP, VEC>(acc, x);
+            }
         }
     }
     float v = acc_collapse<OP, VEC>(acc);
@@ -232,6 +254,41 @@ __global__ void __launch_bounds__(256) reduce_inner_kernel(const RedArgs a) {
         float* dst = a.dst + (size_t)blockIdx.y * a.nout + gt;
         *dst = a.finalize ? rfinal<OP>(a.init, v) : v;
     }
+}
+
+// Packed short rows: source is a dense [nout, R] block (R = 2..8) reduced over its inner axis -- the
+// component axis of RGB / xyz / complex data. One lane per output would issue R scalar loads at a stride
+// of R floats; instead a thread takes FOUR rows = 4R consecutive floats = R aligned float4 loads, sums
+// each row out of registers (all indices are compile-time) and stores one float4.
+template <int OP, int R>
+__global__ void __launch_bounds__(256)
+reduce_rows_packed_kernel(const float* __restrict__ src, float* __restrict__ out, uint32_t nout4, float init) {
+    const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+    if (t >= nout4) return;
+    const float4* p = reinterpret_cast<const float4*>(src) + (size_t)t * R;
+    float x[4 * R];
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        const float4 v = __ldg(p + j);
+        x[4 * j] = v.x, x[4 * j + 1] = v.y, x[4 * j + 2] = v.z, x[4 * j + 3] = v.w;
+    }
+    float o[4];
+#pragma unroll
+    for (int row = 0; row < 4; row++) {
+        float acc = x[row * R];
+#pragma unroll
+        for (int k = 1; k < R; k++) acc = racc<OP>(acc, x[row * R + k]);
+        o[row] = rfinal<OP>(init, acc);
+    }
+    reinterpret_cast<float4*>(out)[t] = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+template <int OP, int R>
+static bool launch_rows_packed(const float* src, float* out, uint64_t nout, float init) {
+    const uint32_t nout4 = (uint32_t)(nout / 4);
+    reduce_rows_packed_kernel<OP, R><<<(nout4 + 255) / 256, 256, 0, rt().stream>>>(src, out, nout4, init);
+    note_launch("reduce_rows_packed");
+    return check_launch("reduce_rows_packed");
 }
 
 // One CTA per (output, split): long reduced extents.
@@ -746,6 +803,20 @@ static bool run_reduce(const float* src, float* out, const AxisList& K, const Ax
         return check_launch("reduce_window");
     }
 
+    // -- dense [nout, R] with a short reduced inner axis --
+    if (!general && K.n == 1 && R.n == 1 && R.stride[0] == 1 && R.extent[0] >= 2 && R.extent[0] <= 8 &&
+        K.stride[0] == (int64_t)R.extent[0] && nout % 4 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)out % 16 == 0) {
+        switch (R.extent[0]) {
+            case 2: return launch_rows_packed<OP, 2>(src, out, nout, init);
+            case 3: return launch_rows_packed<OP, 3>(src, out, nout, init);
+            case 4: return launch_rows_packed<OP, 4>(src, out, nout, init);
+            case 5: return launch_rows_packed<OP, 5>(src, out, nout, init);
+            case 6: return launch_rows_packed<OP, 6>(src, out, nout, init);
+            case 7: return launch_rows_packed<OP, 7>(src, out, nout, init);
+            default: return launch_rows_packed<OP, 8>(src, out, nout, init);
+        }
+    }
+
     const bool outer = K.n > 0 && K.stride[0] == 1 && !(R.n > 0 && R.stride[0] == 1 && K.extent[0] < 8);
     const bool aligned = (uintptr_t)src % 16 == 0;
     for (int d = 0; d < K.n; d++) {
@@ -861,8 +932,12 @@ static bool run_reduce(const float* src, float* out, const AxisList& K, const Ax
         else reduce_inner_cta_kernel<OP, 1><<<grid, 256, 0, st>>>(a);
         note_launch("reduce_inner_cta");
     } else {
-        uint32_t team = pow2_ceil((a.nr_items + 3) / 4);
+        // lanes per output: ~4 loads per lane for 128-bit loads, ~32 for 4-byte loads (measured: 2^20 rows of
+        // 255 floats 3.35 -> 4.48 TB/s; 2^24 rows of 64 floats best at 4), never wider than the inner axis
+        const uint32_t per_lane = r.reduce_loads_per_lane > 0 ? (uint32_t)r.reduce_loads_per_lane : (vec ? 4 : 32);
+        uint32_t team = pow2_ceil((a.nr_items + per_lane - 1) / per_lane);
         if (team > 32) team = 32;
+        while (team > 1 && team > pow2_ceil(a.rext[0])) team >>= 1;
         unsigned gx = (unsigned)(((uint64_t)nout * team + 255) / 256);
 #define AL_TEAM_CASE(T)                                                               \
     case T:                                                                           \
@@ -904,12 +979,26 @@ NDArray* reduce_impl(int redop, const NDArray* src, const size_t* dims, size_t n
     size_t dshape[64];
     for (size_t i = 0; i < nd; i++) dshape[i] = red[i] ? 1 : src->lay->shape[i];
     AxisList K, R;
+    // Kept axes stay in logical order (they define the output layout). The order of the REDUCED axes is
+    // free for the tree kernels, so they are visited by ascending source stride: a transposed or permuted
+    // source then still merges into long unit-stride runs (a full reduce of X.T is one contiguous stream;
+    // in logical order it was a stride-N gather at 0.25 TB/s). The sequential verification mode keeps the
+    // logical order, because there the order IS the point.
+    std::vector<size_t> red_axes;
     for (size_t ax = nd; ax-- > 0;) {  // innermost first
         uint64_t e = src->lay->shape[ax];
         if (e == 1) continue;
-        bool ok = (red[ax] ? R : K).push(e, (int64_t)src->lay->stride[ax]);
-        AL_REQUIRE(ok, "NotImplementedError: reduce layout needs more than %d non-mergeable axes", kMaxDims);
+        if (red[ax]) {
+            red_axes.push_back(ax);
+            continue;
+        }
+        AL_REQUIRE(K.push(e, (int64_t)src->lay->stride[ax]), "NotImplementedError: reduce layout needs more than %d non-mergeable axes", kMaxDims);
     }
+    if (!rt().reduce_sequential)
+        std::stable_sort(red_axes.begin(), red_axes.end(),
+                         [&](size_t x, size_t y) { return src->lay->stride[x] < src->lay->stride[y]; });
+    for (size_t ax : red_axes)
+        AL_REQUIRE(R.push(src->lay->shape[ax], (int64_t)src->lay->stride[ax]), "NotImplementedError: reduce layout needs more than %d non-mergeable axes", kMaxDims);
     if (R.count() >= (1ull << 31)) {
         // More than 2^31-1 reduced elements per output (e.g. a full reduce of config C3's 2^32-element
         // result): halve the widest reduced axis, reduce both halves and combine them elementwise.

@@ -249,3 +249,21 @@ def test_sequential_mode_reproduces_the_reference_bit_for_bit(al, orc, ref, rng,
             assert_bit_equal(al.to_numpy(al.reduce_sum(X, dims=tuple(range(len(shape)))[:1])), want, "vs compiled reference")
     finally:
         lib.al_set_tuning(b"reduce_sequential", 0)
+
+
+@pytest.mark.parametrize("r", [2, 3, 4, 5, 6, 7, 8])
+def test_packed_short_rows(al, orc, rng, r):
+    """[N, r] reduced over the short inner axis (component axis of RGB / xyz / complex data)."""
+    from arraylib_b200._lib import lib
+    x = int_data(rng, (4096, r))
+    X = al.from_numpy(x)
+    for op in ("sum", "max", "min"):
+        got = getattr(al, f"reduce_{op}")(X, dims=(1,))
+        assert lib.al_last_kernel() == b"reduce_rows_packed"
+        assert_bit_equal(al.to_numpy(got), orc.reduce(op, x, (1,)), f"{op} r={r}")
+    f = rng.standard_normal((1028, r)).astype(np.float32)
+    err = np.abs(al.to_numpy(al.reduce_sum(al.from_numpy(f), dims=(1,))).astype(np.float64) - orc.reduce("sum", f, (1,)))
+    assert np.all(err <= sum_tolerance(f, (1,)))
+    y = int_data(rng, (1027, r))  # row count not a multiple of 4: generic path
+    assert_bit_equal(al.to_numpy(al.reduce_sum(al.from_numpy(y), dims=(1,))), orc.reduce("sum", y, (1,)), "odd rows")
+    assert lib.al_last_kernel() != b"reduce_rows_packed"

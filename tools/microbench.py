@@ -191,6 +191,33 @@ def bench_latency():
         print(f"{label:34s} {dt*1e6:8.2f} us per call", flush=True)
 
 
+def bench_reduce_sweep():
+    """reduce_sum over many layouts: look for plans far below the roofline."""
+    n = 1 << 28
+    cases = [((n,), (0,)), ((1 << 14, 1 << 14), (0,)), ((1 << 14, 1 << 14), (1,)), ((1 << 26, 4), (0,)), ((1 << 26, 4), (1,)),
+             ((4, 1 << 26), (0,)), ((4, 1 << 26), (1,)), ((1 << 25, 8), (0,)), ((3, 1 << 20, 85), (0, 2)), ((3, 1 << 20, 85), (1,)),
+             ((1024, 1024, 256), (0, 2)), ((1024, 1024, 256), (1,)), ((1024, 1024, 256), (0, 1)), ((1024, 1024, 256), (1, 2)),
+             ((256, 1024, 1024), (0,)), ((64, 64, 64, 1024), (1, 3)), ((64, 64, 64, 1024), (0, 2)), ((1 << 20, 255), (1,)),
+             ((1 << 20, 255), (0,)), ((1 << 27, 2), (1,)), ((1 << 16, 1 << 12), (1,))]
+    for shape, dims in cases:
+        X = rnd(shape, 1)
+        total = int(np.prod(shape))
+        timed(lambda: X.reduce_sum(dims=dims), 4 * total, f"reduce_sum {shape} dims={dims}", reps=3, warm=1)
+        del X
+    for per_lane in (4, 8, 16, 32):
+        tune(reduce_loads_per_lane=per_lane)
+        for shape, dims in (((1 << 20, 255), (1,)), ((3, 1 << 20, 85), (0, 2)), ((1 << 24, 64), (1,))):
+            X = rnd(shape, 1)
+            timed(lambda: X.reduce_sum(dims=dims), 4 * int(np.prod(shape)), f"loads/lane={per_lane}: reduce_sum {shape} dims={dims}", reps=3, warm=1)
+            del X
+    tune(reduce_loads_per_lane=0)
+    # transposed sources
+    X = rnd((1 << 14, 1 << 14), 2)
+    XT = X.transpose((1, 0))
+    for dims in ((0,), (1,), (0, 1)):
+        timed(lambda: XT.reduce_sum(dims=dims), 4 * (1 << 28), f"reduce_sum of X.T (16384^2) dims={dims}", reps=3, warm=1)
+
+
 def bench_views():
     """Elementwise ops on views that defeat the 128-bit path."""
     n = 1 << 28
