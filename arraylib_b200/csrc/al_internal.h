@@ -33,7 +33,6 @@ struct Runtime {
     uint64_t bytes_in_use = 0;
     // tunables (al_set_tuning)
     long stream_store_min_bytes = 64l << 20;  // outputs at least this big use st.global.cs
-    long ew_unroll = 4;
     long load_policy = 0;      // streaming loads: 0 ld.global.cs, 1 ld.global.nc, 2 nc+L1::no_allocate
     long force_general = 0;    // 1: disable the vector / tile fast paths (tests the fallback)
     long reduce_splits = 0;    // 0 = auto

@@ -241,6 +241,74 @@ __global__ void __launch_bounds__(kEwThreads) ew_nd_kernel(const NdArgs<F::NIN> 
     }
 }
 
+// ---- general N-d kernel, 4 consecutive outputs per thread ------------------------------------------------
+// The fallback for everything the 128-bit plans cannot take (odd inner extents, misaligned rows,
+// arbitrary as_strided operands). Resolving a linear index costs a divmod chain per operand; with
+// one output per thread that put ~60-90 instructions on every element and capped write-bound cases at
+// 1.5-2 TB/s. Here a thread resolves its first index once and then STEPS the multi-index (increment the
+// inner axis, carry when it wraps), so the chain is paid once per four outputs; the four results leave
+// as one 128-bit store when the output is aligned. Neighbouring lanes are 16 bytes apart, so the four
+// loads of a warp cover whole sectors between them (default caching keeps them in L1 in the meantime).
+constexpr int kRun = 4;
+
+template <typename F>
+__global__ void __launch_bounds__(kEwThreads) ew_run_kernel(const NdArgs<F::NIN> a, const F f) {
+    constexpr int NIN = F::NIN;
+    const uint32_t e0 = (blockIdx.x * (uint32_t)kEwThreads + threadIdx.x) * kRun;
+    if (e0 >= a.n_items) return;
+    uint32_t idx[kMaxDims];
+    long long off[NIN];
+#pragma unroll
+    for (int i = 0; i < NIN; i++) off[i] = 0;
+    uint32_t rem = e0;
+#pragma unroll
+    for (int d = 0; d < kMaxDims; d++) {
+        const bool last = (d == a.ndim - 1);
+        if (last) {
+            idx[d] = rem;
+        } else {
+            const uint32_t q = fdiv(rem, a.div[d]);
+            idx[d] = rem - q * a.extent[d];
+            rem = q;
+        }
+#pragma unroll
+        for (int i = 0; i < NIN; i++) off[i] += (long long)idx[d] * a.stride[i][d];
+        if (last) break;
+    }
+    float v[kRun][NIN];
+#pragma unroll
+    for (int j = 0; j < kRun; j++) {
+        if (e0 + j < a.n_items) {
+#pragma unroll
+            for (int i = 0; i < NIN; i++) v[j][i] = __ldg(a.in[i] + off[i]);
+            // step to the next logical element: bump the inner axis, carry while an axis wraps
+#pragma unroll
+            for (int d = 0; d < kMaxDims; d++) {
+                idx[d]++;
+#pragma unroll
+                for (int i = 0; i < NIN; i++) off[i] += a.stride[i][d];
+                if (d == a.ndim - 1 || idx[d] < a.extent[d]) break;
+                idx[d] = 0;
+#pragma unroll
+                for (int i = 0; i < NIN; i++) off[i] -= (long long)a.extent[d] * a.stride[i][d];
+            }
+        }
+    }
+    float r[kRun];
+#pragma unroll
+    for (int j = 0; j < kRun; j++) r[j] = (e0 + j < a.n_items) ? f(v[j]) : 0.0f;
+    float* dst = a.out + e0;
+    if (a.inner_bcast[0] /* reused as: output is 16-byte aligned */ && e0 + kRun <= a.n_items) {
+        const float4 r4 = make_float4(r[0], r[1], r[2], r[3]);
+        if (a.stream_store) __stcs(reinterpret_cast<float4*>(dst), r4);
+        else *reinterpret_cast<float4*>(dst) = r4;
+    } else {
+#pragma unroll
+        for (int j = 0; j < kRun; j++)
+            if (e0 + j < a.n_items) dst[j] = r[j];
+    }
+}
+
 // ---- tiled transpose kernel ----------------------------------------------------------------------
 template <int NIN>
 struct TileArgs {
@@ -776,13 +844,23 @@ static bool launch_nd_one(const F& f, const Folded& fo, const float* const* in, 
         a.inner_bcast[i] = fo.in_stride[i][0] == 0;
         a.reuse[i] = reuse;
     }
-    const long unroll = rt().ew_unroll;
-    auto blocks = [&](int u) { return (unsigned)((n_items + (uint64_t)kEwThreads * u - 1) / ((uint64_t)kEwThreads * u)); };
     cudaStream_t s = rt().stream;
-    if (unroll >= 8) ew_nd_kernel<VEC, 8, F><<<blocks(8), kEwThreads, 0, s>>>(a, f);
-    else if (unroll >= 4) ew_nd_kernel<VEC, 4, F><<<blocks(4), kEwThreads, 0, s>>>(a, f);
-    else if (unroll >= 2) ew_nd_kernel<VEC, 2, F><<<blocks(2), kEwThreads, 0, s>>>(a, f);
-    else ew_nd_kernel<VEC, 1, F><<<blocks(1), kEwThreads, 0, s>>>(a, f);
+    if constexpr (VEC == 4) {
+        // (unroll 1/2/4/8 were swept on C2 and are within 1.5 % of each other; 4 is kept)
+        constexpr int kUnroll = 4;
+        const unsigned blocks = (unsigned)((n_items + (uint64_t)kEwThreads * kUnroll - 1) / ((uint64_t)kEwThreads * kUnroll));
+        ew_nd_kernel<4, kUnroll, F><<<blocks, kEwThreads, 0, s>>>(a, f);
+    } else if (fo.ndim == 1) {
+        // a flat stream that is merely misaligned (or strided): one element per lane is already perfectly
+        // coalesced and needs no index arithmetic (6.57 TB/s on a 4-byte-shifted a+b, vs 6.15 with the run kernel)
+        constexpr int kUnroll = 4;
+        const unsigned blocks = (unsigned)((n_items + (uint64_t)kEwThreads * kUnroll - 1) / ((uint64_t)kEwThreads * kUnroll));
+        ew_nd_kernel<1, kUnroll, F><<<blocks, kEwThreads, 0, s>>>(a, f);
+    } else {
+        a.inner_bcast[0] = (uintptr_t)out % 16 == 0;  // this kernel does not use the per-operand flag; see ew_run_kernel
+        const uint64_t threads = (n_items + kRun - 1) / kRun;
+        ew_run_kernel<F><<<(unsigned)((threads + kEwThreads - 1) / kEwThreads), kEwThreads, 0, s>>>(a, f);
+    }
     note_launch(VEC == 4 ? "ew_nd_vec4" : "ew_nd_scalar");
     return check_launch("ew_nd");
 }

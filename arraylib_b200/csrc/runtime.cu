@@ -368,7 +368,7 @@ int al_set_tuning(const char* key, long value) {
     AL_ENTER;
     std::string k = key ? key : "";
     if (k == "stream_store_min_bytes") g_rt.stream_store_min_bytes = value;
-    else if (k == "ew_unroll") g_rt.ew_unroll = value;
+    else if (k == "ew_unroll") (void)value;  // swept once (profiles/r1_micro_stream_variants.log), now fixed at 4
     else if (k == "load_policy") g_rt.load_policy = value;
     else if (k == "force_general") g_rt.force_general = value;
     else if (k == "reduce_splits") g_rt.reduce_splits = value;

@@ -218,6 +218,20 @@ def bench_reduce_sweep():
         timed(lambda: XT.reduce_sum(dims=dims), 4 * (1 << 28), f"reduce_sum of X.T (16384^2) dims={dims}", reps=3, warm=1)
 
 
+def bench_ew_sweep():
+    """Broadcast patterns: look for elementwise plans far below the roofline (bytes = output + distinct inputs)."""
+    cases = [((1 << 14, 1), (1, 1 << 14)), ((1 << 14, 1 << 14), (1 << 14, 1)), ((1 << 14, 1 << 14), (1, 1 << 14)),
+             ((1 << 28,), (1,)), ((1,), (1 << 28,)), ((64, 1, 512, 512), (1, 16, 1, 1)), ((64, 16, 512, 512), (1, 16, 1, 1)),
+             ((64, 16, 512, 512), (64, 1, 512, 512)), ((64, 16, 512, 512), (512, 1)), ((1 << 20, 1, 16), (1, 16, 16)),
+             ((4096, 1, 4096, 1), (1, 4, 1, 4)), ((1 << 26, 3), (3,)), ((1 << 26, 3), (1 << 26, 1)), ((1 << 22, 1, 7), (1, 9, 7))]
+    for sa, sb in cases:
+        A, B = rnd(sa, 1), rnd(sb, 2)
+        out_shape = np.broadcast_shapes(sa, sb)
+        nbytes = 4 * (int(np.prod(out_shape)) + int(np.prod(sa)) + int(np.prod(sb)))
+        timed(lambda: A + B, nbytes, f"{sa} + {sb}", reps=3, warm=1)
+        del A, B
+
+
 def bench_views():
     """Elementwise ops on views that defeat the 128-bit path."""
     n = 1 << 28
