@@ -3,16 +3,22 @@
 // Replaces the reference loops array_array_op (arraylib/src/arraylib.c:569-589), array_scalar_op
 // (:491-501), array_op (:638-645), array_deep_copy (:248-256) and the where family (:774-838),
 // all of which call offset_indexer (:116-123) per element. Here the layout is folded once on the
-// host (layout.cu) and one of three sm_100a kernels is chosen:
+// host (layout.cu) and run_functor() picks one of these sm_100a kernels:
 //
-//   ew_nd<VEC=4>   inner axis contiguous (stride 1) or broadcast (stride 0) in every operand:
-//                  128-bit loads/stores, outer axes resolved with one mul-hi divmod per axis per
-//                  vector. ndim==1 degenerates to the pure streaming kernel (config C2); stride-0
-//                  outer axes give the broadcast case (config C3).
-//   ew_tile        some operand is unit-stride along a different axis than the output
-//                  (transposed view, config C5b): 32x32 tiles staged through padded shared memory
-//                  so that both the global read and the global write are coalesced.
-//   ew_nd<VEC=1>   anything else (arbitrary as_strided operands): scalar gather.
+//   ew_nd<VEC=4>     inner axis contiguous (stride 1) or broadcast (stride 0) in every operand:
+//                    128-bit loads/stores, outer axes resolved with one mul-hi divmod per axis per
+//                    vector. ndim==1 is the pure streaming kernel (config C2); stride-0 outer axes
+//                    give the row-broadcast case (config C3, second add).
+//   ew_outer         [I,1,W] o [1,J,W]: a 4x4 register tile per thread, 2/4 loads per output instead
+//                    of 2 (config C3, first add).
+//   ew_tile64        an operand is unit-stride along a different axis than the output (transposed
+//                    view, config C5b): 64x64 tiles, 128-bit global accesses on both sides, 4x4
+//                    register transposes, XOR-swizzled shared memory. ew_tile: the 4-byte version for
+//                    extents that are not multiples of 4.
+//   ew_interleave /  the same with a short, densely packed axis ([N,3] <-> [3,N]); ew_tile_rect for
+//   ew_deinterleave  short axes that are not packed.
+//   ew_run           anything else: 4 consecutive outputs per thread, linear index resolved once and
+//                    stepped with carries; ew_nd<VEC=1> for flat (1-D) streams.
 #pragma once
 #include "al_internal.h"
 #include "device_utils.cuh"

@@ -11,9 +11,11 @@
 //                  Config C4a: [64,(512*512),64] -> [64,1,1,64].
 //   reduce_inner   the innermost reduced axis is unit-stride ("reduce-contiguous"): a team of
 //                  2..32 lanes (warp shuffles) or a whole CTA per output. Config C4b: 2^24 x 64.
-//   reduce_window  overlapping as_strided windows (kept stride == reduced stride == 1): each CTA
-//                  stages a tile + halo in shared memory once and forms all window sums from
-//                  per-block prefix/suffix scans. Config C5a.
+//   reduce_rows_packed  dense [N, 2..8] rows: four rows per thread as aligned 128-bit loads.
+//   reduce_window  overlapping as_strided windows (kept stride == reduced stride == 1): persistent CTAs
+//                  stage a tile + halo in shared memory and form all window sums from per-block
+//                  prefix/suffix scans (half-block lanes for w = 8/16/32/64). Config C5a.
+//   reduce_sequential  verification mode: the reference's own summation order, one thread per output.
 //   reduce_finish  second pass when the reduced range was split across CTAs (long reduced
 //                  extent, few outputs): combines the per-split partials in a fixed order.
 //
