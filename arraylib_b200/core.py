@@ -194,7 +194,10 @@ class NDArray:
         return pprepr(self)
 
     def __del__(self):
-        free(self)
+        try:
+            free(self)
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass
 
 
 def _new(ptr) -> NDArray:

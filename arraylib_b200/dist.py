@@ -149,6 +149,95 @@ def _row_major(shape):
     return tuple(reversed(out))
 
 
+class ShardedArray:
+    """A global array whose leading axis is split into contiguous blocks, one per rank ("sharded"), or
+    that every rank holds in full ("replicated"). Arithmetic follows the plan in the module docstring:
+    everything is local except a reduction over axis 0, which ends in one NCCL allreduce."""
+
+    def __init__(self, local, global_shape, placement: str):
+        assert placement in ("sharded", "replicated")
+        self.local, self.shape, self.placement = local, tuple(global_shape), placement
+
+    # -- construction ------------------------------------------------------------------------------
+    @classmethod
+    def scatter(cls, global_array):
+        """Every rank passes the same host array; each uploads only its block of axis 0."""
+        return cls(scatter_from_numpy(global_array), global_array.shape, "sharded")
+
+    @classmethod
+    def replicate(cls, global_array):
+        from . import core
+        return cls(core.from_numpy(global_array), global_array.shape, "replicated")
+
+    # -- helpers -----------------------------------------------------------------------------------
+    def _local_block(self, out_ndim: int):
+        """The local operand to use inside an op whose output is sharded."""
+        if self.placement == "sharded":
+            return self.local
+        if len(self.shape) < out_ndim or self.shape[0] == 1:
+            return self.local  # broadcast along axis 0: the replica is used as it is
+        lo, hi = shard_bounds(self.shape[0], _state["rank"], _state["world"])
+        sl = tuple([slice(lo, hi)] + [slice(0, e) for e in self.shape[1:]])
+        return self.local[sl]  # a view of this rank's rows of the replica
+
+    def _binary(self, name: str, other, reverse: bool = False):
+        from . import core
+        fn = getattr(core, name)
+        if isinstance(other, core.Number):
+            res = fn(other, self.local) if reverse else fn(self.local, other)
+            return ShardedArray(res, self.shape, self.placement)
+        if isinstance(other, core.NDArray):
+            other = ShardedArray(other, other.shape, "replicated")
+        assert isinstance(other, ShardedArray)
+        import numpy as np
+        out_shape = tuple(np.broadcast_shapes(self.shape, other.shape))
+        sharded = "sharded" in (self.placement, other.placement)
+        if sharded:
+            for op in (self, other):
+                if op.placement == "sharded":
+                    assert len(op.shape) == len(out_shape) and op.shape[0] == out_shape[0], \
+                        "a sharded operand must span the output's leading axis"
+            a, b = self._local_block(len(out_shape)), other._local_block(len(out_shape))
+        else:
+            a, b = self.local, other.local
+        res = fn(b, a) if reverse else fn(a, b)
+        return ShardedArray(res, out_shape, "sharded" if sharded else "replicated")
+
+    def __add__(self, o): return self._binary("add", o)
+    def __radd__(self, o): return self._binary("add", o, True)
+    def __sub__(self, o): return self._binary("sub", o)
+    def __rsub__(self, o): return self._binary("sub", o, True)
+    def __mul__(self, o): return self._binary("mul", o)
+    def __rmul__(self, o): return self._binary("mul", o, True)
+    def __truediv__(self, o): return self._binary("div", o)
+    def __rtruediv__(self, o): return self._binary("div", o, True)
+
+    def _reduce(self, op: str, dims):
+        from . import core
+        dims = tuple(range(len(self.shape))) if dims is None else tuple(dims)
+        out_shape = tuple(1 if d in dims else e for d, e in enumerate(self.shape))
+        if self.placement == "replicated":
+            return ShardedArray(getattr(core, f"reduce_{op}")(self.local, dims=dims), out_shape, "replicated")
+        plan = reduce_plan(len(self.shape), dims)
+        return ShardedArray(reduce_sharded(self.local, op, dims), out_shape, plan["output"])
+
+    def reduce_sum(self, *, dims=None): return self._reduce("sum", dims)
+    def reduce_max(self, *, dims=None): return self._reduce("max", dims)
+    def reduce_min(self, *, dims=None): return self._reduce("min", dims)
+
+    # -- materialisation ----------------------------------------------------------------------------
+    def gather(self):
+        """The full array on every rank (allgather; needs equal shards)."""
+        if self.placement == "replicated" or _state["world"] == 1:
+            return self.local
+        assert self.shape[0] % _state["world"] == 0, "allgather needs the leading extent to divide evenly"
+        return allgather(self.local)
+
+    def to_numpy(self):
+        from . import core
+        return core.to_numpy(self.gather())
+
+
 def destroy() -> None:
     from ._lib import lib
 
