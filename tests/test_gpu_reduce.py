@@ -111,7 +111,8 @@ def test_strided_sources(al, orc, rng):
         assert_bit_equal(al.to_numpy(al.reduce_sum(v, dims=dims)), orc.reduce("sum", vn, dims), f"slice {dims}")
 
 
-@pytest.mark.parametrize("n,w", [(1 << 16, 64), (100003, 64), (5000, 8), (20000, 100), (70000, 1024), (300, 64)])
+@pytest.mark.parametrize("n,w", [(1 << 16, 64), (100003, 64), (5000, 8), (20000, 100), (70000, 1024), (300, 64), (30000, 9),
+                                 (50001, 33), (40000, 127), (90000, 500), (8000, 10)])
 def test_sliding_window_view(al, orc, rng, n, w):
     """as_strided (n-w+1, w) with strides (1, 1), reduce over the window axis (config C5a)."""
     base = int_data(rng, (n,))

@@ -115,7 +115,7 @@ def bench_window():
     timed(lambda: base.as_strided(shape=(n - w + 1, w), stride=(1, 1)).reduce_sum(dims=[1]), 4 * n + 4 * (n - w + 1), "window-64 reduce_sum 2^28 whole-block kernel")
     tune(window_whole_blocks=0)
     timed(lambda: base.as_strided(shape=(n - w + 1, w), stride=(1, 1)).reduce_max(dims=[1]), 4 * n + 4 * (n - w + 1), "window-64 reduce_max 2^28")
-    for w2 in (8, 16, 32, 100):
+    for w2 in (8, 16, 32, 24, 100, 500):
         timed(lambda: base.as_strided(shape=(n - w2 + 1, w2), stride=(1, 1)).reduce_sum(dims=[1]), 4 * n + 4 * (n - w2 + 1), f"window-{w2} reduce_sum 2^28", reps=3)
     n2 = 1 << 24
     b2 = rnd((n2,), 1)
