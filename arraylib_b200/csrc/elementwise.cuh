@@ -132,6 +132,7 @@ struct NdArgs {
     unsigned char reuse[NIN];         // operand is re-read (has a stride-0 axis): keep it cached
     unsigned char stream_store;
     unsigned char load_policy;  // 0: ld.global.cs (evict-first), 1: ld.global.nc, 2: nc + L1::no_allocate
+    unsigned char out_aligned;  // ew_run: the output pointer is 16-byte aligned (128-bit stores allowed)
 };
 
 template <int VEC>
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(kEwThreads) ew_run_kernel(const NdArgs<F::NIN>
 #pragma unroll
     for (int j = 0; j < kRun; j++) r[j] = (e0 + j < a.n_items) ? f(v[j]) : 0.0f;
     float* dst = a.out + e0;
-    if (a.inner_bcast[0] /* reused as: output is 16-byte aligned */ && e0 + kRun <= a.n_items) {
+    if (a.out_aligned && e0 + kRun <= a.n_items) {
         const float4 r4 = make_float4(r[0], r[1], r[2], r[3]);
         if (a.stream_store) __stcs(reinterpret_cast<float4*>(dst), r4);
         else *reinterpret_cast<float4*>(dst) = r4;
@@ -863,7 +864,7 @@ static bool launch_nd_one(const F& f, const Folded& fo, const float* const* in, 
         const unsigned blocks = (unsigned)((n_items + (uint64_t)kEwThreads * kUnroll - 1) / ((uint64_t)kEwThreads * kUnroll));
         ew_nd_kernel<1, kUnroll, F><<<blocks, kEwThreads, 0, s>>>(a, f);
     } else {
-        a.inner_bcast[0] = (uintptr_t)out % 16 == 0;  // this kernel does not use the per-operand flag; see ew_run_kernel
+        a.out_aligned = (uintptr_t)out % 16 == 0;
         const uint64_t threads = (n_items + kRun - 1) / kRun;
         ew_run_kernel<F><<<(unsigned)((threads + kEwThreads - 1) / kEwThreads), kEwThreads, 0, s>>>(a, f);
     }
