@@ -27,9 +27,7 @@ class Layout(tp.NamedTuple):  # core.py:40-43
     ndim: int
 
 
-# -------------------------------------------------------------------------------------------------
-# NDArray (core.py:46-199)
-# -------------------------------------------------------------------------------------------------
+# == NDArray (core.py:46-199) ==
 
 
 class NDArray:
@@ -71,91 +69,8 @@ class NDArray:
     def T(self):
         return self.transpose(list(range(self.ndim - 1, -1, -1)))
 
-    # -- methods mirroring the free functions -----------------------------------------------------
-    def reshape(self, shape):
-        return reshape(self, shape)
-
-    def transpose(self, dst):
-        return transpose(self, dst)
-
-    def move_dim(self, src, dst):
-        return move_dim(self, src, dst)
-
-    def ravel(self):
-        return ravel(self)
-
-    def as_strided(self, *, shape, stride):
-        return as_strided(self, shape, stride)
-
-    def reduce_sum(self, *, dims=None):
-        return reduce_sum(self, dims=dims)
-
-    def reduce_max(self, *, dims=None):
-        return reduce_max(self, dims=dims)
-
-    def reduce_min(self, *, dims=None):
-        return reduce_min(self, dims=dims)
-
-    def where(self, lhs, rhs):
-        return where(self, lhs, rhs)
-
-    def cat(self, arrays, *, dims):
-        return cat([self] + list(arrays), dims)
-
-    def apply(self, fn):
-        return apply(fn, self)
-
-    # -- operators ---------------------------------------------------------------------------------
-    def __add__(self, other):
-        return add(self, other)
-
-    def __radd__(self, other):
-        return add(other, self)
-
-    def __sub__(self, other):
-        return sub(self, other)
-
-    def __rsub__(self, other):
-        return sub(other, self)
-
-    def __mul__(self, other):
-        return mul(self, other)
-
-    def __rmul__(self, other):
-        return mul(other, self)
-
-    def __truediv__(self, other):
-        return div(self, other)
-
-    def __rtruediv__(self, other):
-        return div(other, self)
-
-    def __pow__(self, other):
-        return pow(self, other)
-
-    def __neg__(self):
-        return neg(self)
-
-    def __matmul__(self, other):
-        return matmul(self, other)
-
-    def __lt__(self, other):
-        return lt(self, other)
-
-    def __le__(self, other):
-        return le(self, other)
-
-    def __gt__(self, other):
-        return gt(self, other)
-
-    def __ge__(self, other):
-        return ge(self, other)
-
-    def __eq__(self, other):
-        return eq(self, other)
-
-    def __ne__(self, other):
-        return ne(self, other)
+    # Methods and operators that simply forward to the module-level functions are attached below the
+    # function definitions from two tables (_METHOD_TABLE, _OPERATOR_TABLE).
 
     __hash__ = None
 
@@ -219,9 +134,7 @@ def synchronize() -> None:
     check_rc(lib.al_sync())
 
 
-# -------------------------------------------------------------------------------------------------
-# helpers (core.py:207-244)
-# -------------------------------------------------------------------------------------------------
+# == helpers (core.py:207-244) ==
 
 
 def cdiv(a, b):
@@ -257,9 +170,7 @@ def _int_seq(seq, what):
     return tuple(seq)
 
 
-# -------------------------------------------------------------------------------------------------
-# creation (core.py:252-327)
-# -------------------------------------------------------------------------------------------------
+# == creation (core.py:252-327) ==
 
 
 def array(elems) -> NDArray:
@@ -314,9 +225,7 @@ def linspace(start: int, end: int, n: int) -> NDArray:
     return _new(lib.array_linspace(start, end, n))
 
 
-# -------------------------------------------------------------------------------------------------
-# host <-> device (core.py:340-363)
-# -------------------------------------------------------------------------------------------------
+# == host <-> device (core.py:340-363) ==
 
 
 def from_numpy(array, blocking=True) -> NDArray:
@@ -376,9 +285,7 @@ def host_buffer(shape):
     return np.ctypeslib.as_array(raw)[:n].reshape(shape)
 
 
-# -------------------------------------------------------------------------------------------------
-# binary ops (core.py:371-414)
-# -------------------------------------------------------------------------------------------------
+# == binary ops (core.py:371-414) ==
 
 _COMMUTATIVE = {"sum", "mul", "max", "min", "eq", "ne"}
 _MIRROR = {"gt": "lt", "lt": "gt", "ge": "le", "le": "ge"}
@@ -408,20 +315,10 @@ def generate_binary_op(op: str):
     return wrapper
 
 
-add = generate_binary_op("sum")
-sub = generate_binary_op("sub")
-mul = generate_binary_op("mul")
-div = generate_binary_op("div")
-mod = generate_binary_op("mod")
-pow = generate_binary_op("pow")
-max = generate_binary_op("max")
-min = generate_binary_op("min")
-eq = generate_binary_op("eq")
-ne = generate_binary_op("ne")
-gt = generate_binary_op("gt")
-ge = generate_binary_op("ge")
-lt = generate_binary_op("lt")
-le = generate_binary_op("le")
+# module-level names follow the reference (core.py:388-400): `add` is the op called "sum" in the C table
+for _op in BINOPS:
+    globals()["add" if _op == "sum" else _op] = generate_binary_op(_op)
+del _op
 
 
 def matmul(lhs, rhs) -> NDArray:
@@ -436,9 +333,7 @@ def dot(lhs, rhs) -> NDArray:
     return _new(lib.array_array_dot(lhs.buffer, rhs.buffer))
 
 
-# -------------------------------------------------------------------------------------------------
-# unary ufunc table and apply (core.py:422-460)
-# -------------------------------------------------------------------------------------------------
+# == unary ufunc table and apply (core.py:422-460) ==
 
 
 def generate_unary_op(op: str):
@@ -453,25 +348,9 @@ def generate_unary_op(op: str):
     return wrapper
 
 
-neg = generate_unary_op("neg")
-abs = generate_unary_op("abs")
-sqrt = generate_unary_op("sqrt")
-exp = generate_unary_op("exp")
-log = generate_unary_op("log")
-sin = generate_unary_op("sin")
-cos = generate_unary_op("cos")
-tan = generate_unary_op("tan")
-asin = generate_unary_op("asin")
-acos = generate_unary_op("acos")
-atan = generate_unary_op("atan")
-sinh = generate_unary_op("sinh")
-cosh = generate_unary_op("cosh")
-tanh = generate_unary_op("tanh")
-asinh = generate_unary_op("asinh")
-acosh = generate_unary_op("acosh")
-atanh = generate_unary_op("atanh")
-ceil = generate_unary_op("ceil")
-floor = generate_unary_op("floor")
+for _op in UFUNCS:  # neg abs sqrt exp log sin ... floor (core.py:434-452)
+    globals()[_op] = generate_unary_op(_op)
+del _op
 
 
 def apply(fn, array) -> NDArray:
@@ -495,9 +374,7 @@ def apply(fn, array) -> NDArray:
     return _new(lib.array_op_named(code, array.buffer))
 
 
-# -------------------------------------------------------------------------------------------------
-# views (core.py:468-506, 788-802)
-# -------------------------------------------------------------------------------------------------
+# == views (core.py:468-506, 788-802) ==
 
 
 def reshape(array, shape) -> NDArray:
@@ -537,9 +414,7 @@ def as_strided(array, shape, stride) -> NDArray:
     return _new(lib.array_as_strided(array.buffer, C.byref(lay)))
 
 
-# -------------------------------------------------------------------------------------------------
-# indexing (core.py:514-641)
-# -------------------------------------------------------------------------------------------------
+# == indexing (core.py:514-641) ==
 
 
 def _range_args(array, rng):
@@ -619,9 +494,7 @@ def setitem(array, index, value):
     raise NotImplementedError(f"Index type not supported: {index}")
 
 
-# -------------------------------------------------------------------------------------------------
-# copy (core.py:649-653)
-# -------------------------------------------------------------------------------------------------
+# == copy (core.py:649-653) ==
 
 
 def copy(array, deep=False) -> NDArray:
@@ -629,9 +502,7 @@ def copy(array, deep=False) -> NDArray:
     return _new(fn(array.buffer))
 
 
-# -------------------------------------------------------------------------------------------------
-# reductions (core.py:661-694)
-# -------------------------------------------------------------------------------------------------
+# == reductions (core.py:661-694) ==
 
 
 def _dims_arg(array, dims):
@@ -667,9 +538,7 @@ reduce_max = generate_reduce_op("max")
 reduce_min = generate_reduce_op("min")
 
 
-# -------------------------------------------------------------------------------------------------
-# where / cat (core.py:702-748)
-# -------------------------------------------------------------------------------------------------
+# == where / cat (core.py:702-748) ==
 
 
 def where(cond, lhs, rhs) -> NDArray:
@@ -710,9 +579,7 @@ def cat(arrays, dims=None) -> NDArray:
     return out
 
 
-# -------------------------------------------------------------------------------------------------
-# printing (core.py:756-780): formats a host copy
-# -------------------------------------------------------------------------------------------------
+# == printing (core.py:756-780): formats a host copy ==
 
 
 def pprepr(array) -> str:
@@ -738,3 +605,41 @@ def ppstr(array) -> str:
 
     emit(host)
     return out.getvalue()
+
+
+# == NDArray methods / operators that forward to the functions above (core.py:76-185 in the reference) ==
+
+_METHOD_TABLE = {
+    # name: (function, how the method's arguments map onto the function's)
+    "reshape": lambda self, shape: reshape(self, shape),
+    "transpose": lambda self, dst: transpose(self, dst),
+    "move_dim": lambda self, src, dst: move_dim(self, src, dst),
+    "ravel": lambda self: ravel(self),
+    "as_strided": lambda self, *, shape, stride: as_strided(self, shape, stride),
+    "reduce_sum": lambda self, *, dims=None: reduce_sum(self, dims=dims),
+    "reduce_max": lambda self, *, dims=None: reduce_max(self, dims=dims),
+    "reduce_min": lambda self, *, dims=None: reduce_min(self, dims=dims),
+    "where": lambda self, lhs, rhs: where(self, lhs, rhs),
+    "cat": lambda self, arrays, *, dims: cat([self] + list(arrays), dims),
+    "apply": lambda self, fn: apply(fn, self),
+}
+_OPERATOR_TABLE = {  # dunder stem -> (function, reflected variant exists)
+    "add": (add, True), "sub": (sub, True), "mul": (mul, True), "truediv": (div, True), "pow": (pow, False),
+    "matmul": (matmul, False), "lt": (lt, False), "le": (le, False), "gt": (gt, False), "ge": (ge, False),
+    "eq": (eq, False), "ne": (ne, False),
+}
+
+
+def _attach_forwarders():
+    for name, impl in _METHOD_TABLE.items():
+        impl.__name__ = impl.__qualname__ = name
+        setattr(NDArray, name, impl)
+    for stem, (fn, reflected) in _OPERATOR_TABLE.items():
+        setattr(NDArray, f"__{stem}__", (lambda f: lambda self, other: f(self, other))(fn))
+        if reflected:
+            setattr(NDArray, f"__r{stem}__", (lambda f: lambda self, other: f(other, self))(fn))
+    NDArray.__neg__ = lambda self: neg(self)
+    NDArray.__hash__ = None  # __eq__ is elementwise, like the reference
+
+
+_attach_forwarders()
