@@ -47,6 +47,7 @@ struct Runtime {
     long stream_tma = 0;       // 1: contiguous add/mul through the cp.async.bulk + mbarrier pipeline (experiment)
     long interleave = 1;       // 0: short-axis transposes always use the rectangular tile kernel
     long outer_tile = 1;       // 0: do not use the register-tiled outer-broadcast kernel
+    long peer_collective = 1;  // 0: cross-GPU reductions go through ncclAllReduce instead of the peer-memory windows
 };
 Runtime& rt();
 bool ensure_init();  // lazily al_init(-1); false (with error set) on failure

@@ -25,6 +25,7 @@
 
 #include "al_internal.h"
 #include "device_utils.cuh"
+#include "peer.cuh"
 
 namespace al {
 
@@ -70,6 +71,7 @@ struct RedArgs {
     uint32_t r_per_split;
     float init;
     int finalize;
+    PeerMap peer;        // world > 0: final stores go to the owners' peer slots, un-finalised (peer.cuh)
 };
 
 __device__ __forceinline__ long long kept_offset(const RedArgs& a, uint32_t g) {
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(256) reduce_outer_kernel(const RedArgs a) {
         for (uint32_t y = 1; y < blockDim.y; y++) acc_into<OP, VEC>(acc, sm[y * blockDim.x + threadIdx.x]);
     }
     if (!live) return;
-    float* dst = a.dst + (size_t)blockIdx.y * a.nout + (size_t)g * VEC;
+    float* dst = a.peer.world ? peer_dst(a.peer, g * VEC) : a.dst + (size_t)blockIdx.y * a.nout + (size_t)g * VEC;
     if constexpr (VEC == 1) {
         dst[0] = a.finalize ? rfinal<OP>(a.init, acc.v) : acc.v;
     } else {
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(256) reduce_sequential_kernel(const RedArgs a)
 template <int OP>
 __global__ void __launch_bounds__(256)
 reduce_finish_kernel(const float* __restrict__ partial, float* __restrict__ out, uint32_t nout, uint32_t splits,
-                     float init) {
+                     float init, const PeerMap peer) {
     if (nout <= 2048) {  // one warp per output, lanes stride over the splits
         const uint32_t o = (blockIdx.x * 256u + threadIdx.x) >> 5, lane = threadIdx.x & 31;
         float v = rident<OP>();
@@ -365,13 +367,17 @@ reduce_finish_kernel(const float* __restrict__ partial, float* __restrict__ out,
             for (uint32_t s = lane; s < splits; s += 32) v = racc<OP>(v, partial[(size_t)s * nout + o]);
 #pragma unroll
         for (int k = 16; k > 0; k >>= 1) v = racc<OP>(v, __shfl_down_sync(0xffffffffu, v, k));
-        if (o < nout && lane == 0) out[o] = rfinal<OP>(init, v);
+        if (o < nout && lane == 0) {
+            if (peer.world) *peer_dst(peer, o) = v;
+            else out[o] = rfinal<OP>(init, v);
+        }
     } else {
         const uint32_t o = blockIdx.x * 256u + threadIdx.x;
         if (o >= nout) return;
         float v = rident<OP>();
         for (uint32_t s = 0; s < splits; s++) v = racc<OP>(v, partial[(size_t)s * nout + o]);
-        out[o] = rfinal<OP>(init, v);
+        if (peer.world) *peer_dst(peer, o) = v;
+        else out[o] = rfinal<OP>(init, v);
     }
 }
 
@@ -737,8 +743,16 @@ static uint32_t pow2_ceil(uint32_t v) {
 }
 
 template <int OP>
-static bool run_reduce(const float* src, float* out, const AxisList& K, const AxisList& R, float init) {
+static bool run_reduce(const float* src, float* out, const AxisList& K, const AxisList& R, float init,
+                       const PeerMap* peer = nullptr, bool* peer_used = nullptr) {
     Runtime& r = rt();
+    if (peer) {
+        // Only the output-contiguous plan carries the peer epilogue (a reduction over the sharded leading
+        // axis keeps a unit-stride inner axis); anything else is reduced locally and pushed afterwards.
+        *peer_used = false;
+        const bool outer_plan = K.n > 0 && K.stride[0] == 1 && !(R.n > 0 && R.stride[0] == 1);
+        if (r.reduce_sequential || !outer_plan) return true;
+    }
     cudaStream_t st = r.stream;
     const uint64_t nout = K.count(), rtot = R.count();
     if (nout >= (1ull << 31) || rtot >= (1ull << 31)) {
@@ -870,14 +884,19 @@ static bool run_reduce(const float* src, float* out, const AxisList& K, const Ax
         if (splits > 65535) splits = 65535;
         a.r_per_split = (uint32_t)((rtot + splits - 1) / splits);
         splits = (unsigned)((rtot + a.r_per_split - 1) / a.r_per_split);
-        a.finalize = splits == 1;
+        a.finalize = splits == 1 && !peer;
+        PeerMap finish_peer;
+        memset(&finish_peer, 0, sizeof finish_peer);
         if (splits > 1) {
             partial = (float*)device_alloc((size_t)splits * nout * sizeof(float));
             if (!partial) return false;
             a.dst = partial;
+            if (peer) finish_peer = *peer;
         } else {
             a.dst = out;
+            if (peer) a.peer = *peer;
         }
+        if (peer) *peer_used = true;
         size_t smem = TY > 1 ? (size_t)256 * sizeof(float) * VEC : 0;
         dim3 grid(gx, splits), block(TX, TY);
         if (vec) reduce_outer_kernel<OP, 4><<<grid, block, smem, st>>>(a);
@@ -886,7 +905,7 @@ static bool run_reduce(const float* src, float* out, const AxisList& K, const Ax
         if (!check_launch("reduce_outer")) return false;
         if (splits > 1) {
             unsigned fb = nout <= 2048 ? (unsigned)((nout * 32 + 255) / 256) : (unsigned)((nout + 255) / 256);
-            reduce_finish_kernel<OP><<<fb, 256, 0, st>>>(partial, out, (uint32_t)nout, splits, init);
+            reduce_finish_kernel<OP><<<fb, 256, 0, st>>>(partial, out, (uint32_t)nout, splits, init, finish_peer);
             note_launch("reduce_finish");
             device_free(partial);
             return check_launch("reduce_finish");
@@ -960,7 +979,9 @@ static bool run_reduce(const float* src, float* out, const AxisList& K, const Ax
     if (!check_launch("reduce_inner")) return false;
     if (splits > 1) {
         unsigned fb = nout <= 2048 ? (unsigned)((nout * 32 + 255) / 256) : (unsigned)((nout + 255) / 256);
-        reduce_finish_kernel<OP><<<fb, 256, 0, st>>>(partial, out, (uint32_t)nout, splits, init);
+        PeerMap no_peer;
+        memset(&no_peer, 0, sizeof no_peer);
+        reduce_finish_kernel<OP><<<fb, 256, 0, st>>>(partial, out, (uint32_t)nout, splits, init, no_peer);
         note_launch("reduce_finish");
         device_free(partial);
         return check_launch("reduce_finish");
@@ -968,19 +989,19 @@ static bool run_reduce(const float* src, float* out, const AxisList& K, const Ax
     return true;
 }
 
-NDArray* reduce_impl(int redop, const NDArray* src, const size_t* dims, size_t ndims, float init, bool custom_init) {
-    if (!valid(src, "array_reduce")) return nullptr;
+// Split the source axes into the kept list K and the reduced list R (each innermost first, merged
+// where contiguous) and produce the keepdims output shape.
+static bool build_axes(int redop, const NDArray* src, const size_t* dims, size_t ndims, AxisList& K, AxisList& R,
+                       size_t* dshape, bool* red) {
     AL_REQUIRE(redop >= 0 && redop < AL_REDOP_COUNT, "ValueError: unknown reduce op %d", redop);
     const size_t nd = src->lay->ndim;
     AL_REQUIRE(nd <= 64, "ValueError: too many dimensions");
-    bool red[64] = {false};
+    for (size_t i = 0; i < 64; i++) red[i] = false;
     for (size_t i = 0; i < ndims; i++) {
         AL_REQUIRE(dims[i] < nd, "ValueError: out of bounds");
         red[dims[i]] = true;
     }
-    size_t dshape[64];
     for (size_t i = 0; i < nd; i++) dshape[i] = red[i] ? 1 : src->lay->shape[i];
-    AxisList K, R;
     // Kept axes stay in logical order (they define the output layout). The order of the REDUCED axes is
     // free for the tree kernels, so they are visited by ascending source stride: a transposed or permuted
     // source then still merges into long unit-stride runs (a full reduce of X.T is one contiguous stream;
@@ -1001,6 +1022,16 @@ NDArray* reduce_impl(int redop, const NDArray* src, const size_t* dims, size_t n
                          [&](size_t x, size_t y) { return src->lay->stride[x] < src->lay->stride[y]; });
     for (size_t ax : red_axes)
         AL_REQUIRE(R.push(src->lay->shape[ax], (int64_t)src->lay->stride[ax]), "NotImplementedError: reduce layout needs more than %d non-mergeable axes", kMaxDims);
+    return true;
+}
+
+NDArray* reduce_impl(int redop, const NDArray* src, const size_t* dims, size_t ndims, float init, bool custom_init) {
+    if (!valid(src, "array_reduce")) return nullptr;
+    const size_t nd = src->lay->ndim;
+    bool red[64];
+    size_t dshape[64];
+    AxisList K, R;
+    if (!build_axes(redop, src, dims, ndims, K, R, dshape, red)) return nullptr;
     if (R.count() >= (1ull << 31)) {
         // More than 2^31-1 reduced elements per output (e.g. a full reduce of config C3's 2^32-element
         // result): halve the widest reduced axis, reduce both halves and combine them elementwise.
@@ -1048,6 +1079,25 @@ NDArray* reduce_impl(int redop, const NDArray* src, const size_t* dims, size_t n
         return nullptr;
     }
     return out;
+}
+
+// Local stage of a cross-GPU reduction: the same planning as reduce_impl, but the final stores of the
+// output-contiguous kernel go straight into the owners' peer slots, un-finalised (peer.cuh).
+bool reduce_into_peers(int redop, const NDArray* src, const size_t* dims, size_t ndims, const PeerMap& map, bool* used) {
+    *used = false;
+    if (!valid(src, "al_comm_reduce")) return false;
+    bool red[64];
+    size_t dshape[64];
+    AxisList K, R;
+    if (!build_axes(redop, src, dims, ndims, K, R, dshape, red)) return false;
+    if (K.count() >= (1ull << 31) || R.count() >= (1ull << 31)) return true;  // caller takes the two-step route
+    const float ident[AL_REDOP_COUNT] = {0.0f, -INFINITY, INFINITY, 1.0f};
+    switch (redop) {
+        case AL_RSUM: return run_reduce<AL_RSUM>(src->ptr, nullptr, K, R, ident[redop], &map, used);
+        case AL_RMAX: return run_reduce<AL_RMAX>(src->ptr, nullptr, K, R, ident[redop], &map, used);
+        case AL_RMIN: return run_reduce<AL_RMIN>(src->ptr, nullptr, K, R, ident[redop], &map, used);
+        default: return run_reduce<AL_RPROD>(src->ptr, nullptr, K, R, ident[redop], &map, used);
+    }
 }
 
 }  // namespace al

@@ -98,14 +98,24 @@ def allreduce(array, op: str = "sum"):
 
 
 def reduce_sharded(array, op: str = "sum", dims=None):
-    """reduce_<op> of a leading-axis shard: local kernel, then one allreduce iff axis 0 is reduced."""
+    """reduce_<op> of a leading-axis shard. Local unless axis 0 is reduced; then ONE collective call
+    (al_comm_reduce): the local kernel stores its partial straight into the other GPUs' peer windows and
+    the partials are combined in rank order (ncclAllReduce when the windows cannot be mapped)."""
     from . import core
+    from ._lib import REDOPS, lib
 
     plan = reduce_plan(array.ndim, dims)
-    part = getattr(core, f"reduce_{op}")(array, dims=plan["local_dims"])
-    if plan["collective"]:
-        allreduce(part, op)
-    return part
+    if not plan["collective"] or _state["world"] == 1:
+        return getattr(core, f"reduce_{op}")(array, dims=plan["local_dims"])
+    dims_c, n = core._dims_arg(array, plan["local_dims"])
+    return core._new(lib.al_comm_reduce(REDOPS.index(op), array.buffer, dims_c, n))
+
+
+def transport() -> str:
+    """How cross-GPU reductions travel: 'peer-memory', 'nccl (<why>)' or 'single process'."""
+    from ._lib import lib
+
+    return lib.al_comm_transport().decode()
 
 
 def scatter_from_numpy(global_array):

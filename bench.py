@@ -372,6 +372,7 @@ def run_gpu(args):
         except Exception as exc:  # the checker is optional for the GPU number
             cpu_baseline = {"error": repr(exc)}
 
+    transport = dist.transport()
     if tdist is not None:
         dist.destroy()
         tdist.destroy_process_group()
@@ -383,7 +384,8 @@ def run_gpu(args):
         "dtype": "f32", "data": "synthetic (standard-normal float32, random-init, no datasets)",
         "config": {"workload": "C2+C3+C4+C5 hot-path suite at the BASELINE shapes" + ("" if args.scale == 1 else f" / scale {args.scale}"),
                    "shapes": {"c2_n": n2, "c3": f"[{c3[0]},1,{c3[2]}]+[1,{c3[1]},{c3[2]}]+[{c3[2]}]", "c4": list(c4), "c5a_n": n5, "c5a_window": w, "c5b": [m5, m5]},
-                   "sharding": "leading axis, one shard of the named shape per GPU", "l2_policy": "inputs larger than L2 (>=1 GiB per operand); no flush",
+                   "sharding": "leading axis, one shard of the named shape per GPU",
+                   "cross_gpu_reduce": transport, "l2_policy": "inputs larger than L2 (>=1 GiB per operand); no flush",
                    "algorithmic_bytes_per_step_per_gpu": int(step_bytes)},
         "pct_of_8TBs_per_gpu": round(100 * value / world / NOMINAL_GBS, 1),
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "ops": per_op, "fused_chain": fused, "e2e": e2e, "cpu_baseline": cpu_baseline,

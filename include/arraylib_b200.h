@@ -230,11 +230,18 @@ NDArray* array_array_scalar_where(const NDArray* cond, const NDArray* lhs, f32 r
 NDArray* array_scalar_array_where(const NDArray* cond, f32 lhs, const NDArray* rhs);
 NDArray* array_scalar_scalar_where(const NDArray* cond, f32 lhs, f32 rhs);
 
-/* ---- multi-GPU (new): one process per GPU, NCCL only for partial-sum exchange -------------- */
+/* ---- multi-GPU (new): one process per GPU; the only exchange step is the partial-result combine of a
+ * reduction that crosses the sharded leading axis (the reference has no multi-device path,
+ * its nearest relative is the per-thread accumulator merge, arraylib.c:732-750) ------------------------- */
 int al_comm_unique_id(char out[128]);                       /* rank 0: ncclGetUniqueId */
 int al_comm_init(const char id[128], int rank, int world);  /* ncclCommInitRank on the bound device */
 int al_comm_allreduce(NDArray* a, int redop);               /* in place over a contiguous array (sum/max/min/prod) */
 int al_comm_allgather(const NDArray* shard, NDArray* full); /* concatenate equal leading-dim shards */
+/* reduce_<op>(shard, dims) completed across ranks when dims contains axis 0; the full keepdims result on every
+ * rank. One node: the local reduce kernel stores into CUDA-IPC peer windows over NVLink and the partials are
+ * combined in rank order (deterministic); otherwise local reduce + ncclAllReduce. Collective call. */
+NDArray* al_comm_reduce(int redop, const NDArray* shard, const size_t* reduce_dims, size_t reduce_ndim);
+const char* al_comm_transport(void);                        /* "peer-memory" | "nccl (<why>)" | "single process" */
 int al_comm_destroy(void);
 
 #ifdef __cplusplus

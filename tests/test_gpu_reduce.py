@@ -268,3 +268,20 @@ def test_packed_short_rows(al, orc, rng, r):
     y = int_data(rng, (1027, r))  # row count not a multiple of 4: generic path
     assert_bit_equal(al.to_numpy(al.reduce_sum(al.from_numpy(y), dims=(1,))), orc.reduce("sum", y, (1,)), "odd rows")
     assert lib.al_last_kernel() != b"reduce_rows_packed"
+
+
+def test_cross_gpu_entry_point_is_the_local_reduce_in_a_single_process(al, orc, rng):
+    """al_comm_reduce (the collective behind dist.reduce_sharded) degenerates to array_reduce_<op> when there is
+    no communicator; the N > 1 peer-memory path is covered by tools/dist_check.py under torchrun."""
+    from arraylib_b200 import core, dist
+    from arraylib_b200._lib import REDOPS, lib
+
+    x = rng.integers(-8, 9, size=(6, 5, 64)).astype(np.float32)
+    a = al.from_numpy(x)
+    assert dist.transport() == "single process"
+    for op in ("sum", "max", "min"):
+        for dims in [(0,), (0, 2), (1,), (0, 1, 2)]:
+            dims_c, n = core._dims_arg(a, dims)
+            got = core._new(lib.al_comm_reduce(REDOPS.index(op), a.buffer, dims_c, n))
+            assert_bit_equal(al.to_numpy(got), orc.reduce(op, x, dims))
+            assert_bit_equal(al.to_numpy(dist.reduce_sharded(a, op, dims)), orc.reduce(op, x, dims))

@@ -75,6 +75,89 @@ check("ShardedArray reduce (0,2)", r.to_numpy(), orc.reduce("sum", X, (0, 2)))
 r = (SX - 1.0).reduce_max(dims=(1, 3))
 assert r.placement == "sharded"
 check("ShardedArray reduce_max (1,3)", r.to_numpy(), orc.reduce("max", orc.binary("sub", X, 1.0), (1, 3)))
+
+# ---- the cross-GPU reduce itself: peer-memory windows (default) against the oracle, against NCCL, across ranks ----
+import ctypes as C  # noqa: E402
+import hashlib  # noqa: E402
+
+if rank == 0:
+    print("transport before first use:", dist.transport(), flush=True)
+
+
+def same_on_all_ranks(name, host):
+    box = [None] * world
+    td.all_gather_object(box, hashlib.sha1(np.ascontiguousarray(host).tobytes()).hexdigest())
+    ok = len(set(box)) == 1
+    if not ok:
+        fails.append(name + " (ranks differ)")
+    if rank == 0 and not ok:
+        print(f"{name:28s} RANKS DIFFER", flush=True)
+
+
+for shape, dims, op in [((L, 7, 13), (0,), "sum"), ((L, 7, 13), (0,), "max"), ((L, 7, 13), (0,), "min"), ((L, 5, 64), (0, 1), "sum"),
+                        ((L, 33), (0,), "sum"), ((L, 4096), (0,), "sum"), ((L, 3, 1000), (0, 2), "sum"), ((L, 64), (0, 1), "sum"),
+                        ((L,), (0,), "sum"), ((L, 6, 40), (0, 1, 2), "max"), ((L, 1, 260), (0,), "min")]:
+    G = rng.integers(-8, 9, size=shape).astype(np.float32)
+    Gs = dist.scatter_from_numpy(G)
+    for rep in range(3):  # repeated calls: the window epochs advance, the slots are reused
+        got = al.to_numpy(dist.reduce_sharded(Gs, op, dims))
+        check(f"peer {op} {shape} {dims} #{rep}", got, orc.reduce(op, G, dims))
+        same_on_all_ranks(f"peer {op} {shape} {dims}", got)
+# transposed shard: kept axis not unit-stride -> local reduce + push
+G = rng.integers(-8, 9, size=(L, 48, 20)).astype(np.float32)
+Gt = dist.scatter_from_numpy(G).transpose((0, 2, 1))
+check("peer sum transposed shard", al.to_numpy(dist.reduce_sharded(Gt, "sum", (0,))), orc.reduce("sum", np.transpose(G, (0, 2, 1)), (0,)))
+# random normals: rank-ordered combine is deterministic (same bits on every rank and on every run) and within the
+# stated reduce_sum tolerance of the oracle
+G = rng.standard_normal((L, 64, 1024)).astype(np.float32)
+Gs = dist.scatter_from_numpy(G)
+first = al.to_numpy(dist.reduce_sharded(Gs, "sum", (0,)))
+same_on_all_ranks("peer normal sum", first)
+for rep in range(3):
+    check(f"peer normal sum rerun #{rep}", al.to_numpy(dist.reduce_sharded(Gs, "sum", (0,))), first)
+want = orc.reduce("sum", G, (0,))
+bound = 2 * L * 2.0**-24 * np.abs(G).sum(axis=0, keepdims=True)
+ok = bool(np.all(np.abs(first.astype(np.float64) - want) <= bound))
+if not ok:
+    fails.append("peer normal sum tolerance")
+if rank == 0:
+    print(f"{'peer normal sum tolerance':28s} {'ok' if ok else 'MISMATCH'}", flush=True)
+# more outputs than the first window holds (2 x 64 MiB): the windows are remapped collectively
+big = rng.integers(-8, 9, size=(2 * world, (1 << 24) + 8)).astype(np.float32)
+bs = dist.scatter_from_numpy(big)
+check("peer sum after window remap", al.to_numpy(dist.reduce_sharded(bs, "sum", (0,))), big.sum(axis=0, keepdims=True, dtype=np.float32))
+del bs, big
+if rank == 0:
+    print("transport:", dist.transport(), flush=True)
+
+# timing at the C4 shape of the bench (one [64,512,512,64]-proportioned slab per rank is 4 GiB; use a quarter)
+T = al.from_numpy(rng.standard_normal((16, 512, 512, 64)).astype(np.float32))
+ms = C.c_float()
+for mode in (1, 0, 1):
+    lib.al_set_tuning(b"peer_collective", mode)
+    for _ in range(3):
+        dist.reduce_sharded(T, "sum", (0,))
+    al.synchronize() if hasattr(al, "synchronize") else lib.al_sync()
+    td.barrier()
+    lib.al_timer_start()
+    for _ in range(10):
+        dist.reduce_sharded(T, "sum", (0,))
+    lib.al_timer_stop(C.byref(ms))
+    t = torch.tensor([ms.value / 10], device="cuda")
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+    if rank == 0:
+        print(f"reduce dims=(0,) of a (16,512,512,64) slab per rank, 2^24 outputs: {'peer-memory' if mode else 'nccl':12s} {t.item():.4f} ms", flush=True)
+lib.al_set_tuning(b"peer_collective", 1)
+a1 = al.to_numpy(dist.reduce_sharded(T, "sum", (0,)))
+lib.al_set_tuning(b"peer_collective", 0)
+a0 = al.to_numpy(dist.reduce_sharded(T, "sum", (0,)))
+lib.al_set_tuning(b"peer_collective", 1)
+ok = bool(np.allclose(a1, a0, rtol=1e-5, atol=1e-4))
+if not ok:
+    fails.append("peer vs nccl")
+if rank == 0:
+    print(f"{'peer vs nccl (allclose)':28s} {'ok' if ok else 'MISMATCH'}", flush=True)
+
 flag = torch.tensor([len(fails)], device="cuda")
 td.all_reduce(flag)
 dist.destroy()
