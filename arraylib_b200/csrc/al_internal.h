@@ -37,6 +37,7 @@ struct Runtime {
     long force_general = 0;    // 1: disable the vector / tile fast paths (tests the fallback)
     long reduce_splits = 0;    // 0 = auto
     long reduce_loads_per_lane = 0;  // reduce_inner team sizing: reduced items per lane (0 = default 4)
+    long reduce_peel = 1;      // 0: misaligned unit-stride rows use scalar lanes instead of masked aligned float4s
     long reduce_sequential = 0;  // 1: one thread per output, the reference's summation order (bit-exact, slow)
     long disable_window = 0;
     long window_whole_blocks = 0;  // 1: fixed-w windows use the whole-block scan kernel instead of the half-block one

@@ -133,6 +133,12 @@ struct NdArgs {
     unsigned char stream_store;
     unsigned char load_policy;  // 0: ld.global.cs (evict-first), 1: ld.global.nc, 2: nc + L1::no_allocate
     unsigned char out_aligned;  // ew_run: the output pointer is 16-byte aligned (128-bit stores allowed)
+    // ew_run: how each operand is addressed. 0 = congruent with the output and 16-byte aligned (one 128-bit load),
+    // 1 = "block broadcast": unit-stride over one run of axes and stride 0 over all others, so that the offset
+    // of output element e is (e / blk_inner) mod blk_len, 2 = anything else (row offsets + inner stride).
+    unsigned char mode[NIN];
+    uint32_t blk_inner[NIN], blk_len[NIN];
+    FastDiv blk_inner_div[NIN], blk_len_div[NIN];
 };
 
 template <int VEC>
@@ -250,54 +256,104 @@ __global__ void __launch_bounds__(kEwThreads) ew_nd_kernel(const NdArgs<F::NIN> 
 
 // ---- general N-d kernel, 4 consecutive outputs per thread ------------------------------------------------
 // The fallback for everything the 128-bit plans cannot take (odd inner extents, misaligned rows,
-// arbitrary as_strided operands). Resolving a linear index costs a divmod chain per operand; with
-// one output per thread that put ~60-90 instructions on every element and capped write-bound cases at
-// 1.5-2 TB/s. Here a thread resolves its first index once and then STEPS the multi-index (increment the
-// inner axis, carry when it wraps), so the chain is paid once per four outputs; the four results leave
-// as one 128-bit store when the output is aligned. Neighbouring lanes are 16 bytes apart, so the four
-// loads of a warp cover whole sectors between them (default caching keeps them in L1 in the meantime).
+// arbitrary as_strided operands). Resolving a linear index costs a divmod chain per operand; with one
+// output per thread that put ~60-90 instructions on every element and capped write-bound cases at
+// 1.5-2 TB/s. Here a thread owns 4 consecutive outputs (one 128-bit store when the output is aligned)
+// and each operand is addressed in the cheapest way its layout allows:
+//   mode 0  congruent with the output (the big stream of "(N,3) + (3,)"): one 128-bit load, no index;
+//   mode 1  block broadcast -- unit-stride over one run of axes, stride 0 over the rest, which is what
+//           NumPy-style broadcasting of a contiguous array produces when its non-1 extents are adjacent
+//           ((3,), (N,1), (1,C,1,1), a scalar ...): offset(e) = (e / inner) mod len, resolved with two
+//           mul-hi divisions per THREAD and stepped with two compare/selects per element;
+//   mode 2  anything else: the 4 outputs lie in at most three consecutive rows (a row = one pass over
+//           the inner axis), so the offsets of rows q, q+1 (q+2 only when the inner extent is 2) are
+//           resolved once and every element is row offset + inner index * inner stride.
 constexpr int kRun = 4;
+
+template <int NIN>
+__device__ __forceinline__ void run_row_offsets(const NdArgs<NIN>& a, uint32_t q, long long* off) {
+#pragma unroll
+    for (int i = 0; i < NIN; i++) off[i] = 0;
+    uint32_t rem = q;
+#pragma unroll
+    for (int d = 1; d < kMaxDims; d++) {
+        if (d >= a.ndim) break;
+        uint32_t idx;
+        if (d == a.ndim - 1) {
+            idx = rem;
+        } else {
+            const uint32_t qq = fdiv(rem, a.div[d]);
+            idx = rem - qq * a.extent[d];
+            rem = qq;
+        }
+#pragma unroll
+        for (int i = 0; i < NIN; i++) off[i] += (long long)idx * a.stride[i][d];
+    }
+}
 
 template <typename F>
 __global__ void __launch_bounds__(kEwThreads) ew_run_kernel(const NdArgs<F::NIN> a, const F f) {
     constexpr int NIN = F::NIN;
     const uint32_t e0 = (blockIdx.x * (uint32_t)kEwThreads + threadIdx.x) * kRun;
     if (e0 >= a.n_items) return;
-    uint32_t idx[kMaxDims];
-    long long off[NIN];
+    const bool full = a.out_aligned && e0 + kRun <= a.n_items;
+    float v[kRun][NIN];
+    bool general = false;
 #pragma unroll
-    for (int i = 0; i < NIN; i++) off[i] = 0;
-    uint32_t rem = e0;
+    for (int i = 0; i < NIN; i++) {
+        if (a.mode[i] == 0 && full) {
+            const float4 d = __ldcs(reinterpret_cast<const float4*>(a.in[i] + e0));
+            v[0][i] = d.x, v[1][i] = d.y, v[2][i] = d.z, v[3][i] = d.w;
+        } else if (a.mode[i] <= 1) {
+            // mode 0 on a ragged tail is the block formula with inner = 1, len = all (set up by the host)
+            const uint32_t inner = a.blk_inner[i], len = a.blk_len[i];
+            const uint32_t t = fdiv(e0, a.blk_inner_div[i]);
+            uint32_t c = e0 - t * inner;
+            uint32_t o = t - fdiv(t, a.blk_len_div[i]) * len;
 #pragma unroll
-    for (int d = 0; d < kMaxDims; d++) {
-        const bool last = (d == a.ndim - 1);
-        if (last) {
-            idx[d] = rem;
+            for (int j = 0; j < kRun; j++) {
+                if (e0 + j < a.n_items) v[j][i] = __ldg(a.in[i] + o);
+                if (++c == inner) {
+                    c = 0;
+                    if (++o == len) o = 0;
+                }
+            }
         } else {
-            const uint32_t q = fdiv(rem, a.div[d]);
-            idx[d] = rem - q * a.extent[d];
-            rem = q;
+            general = true;
+        }
+    }
+    if (general) {
+        const uint32_t ext0 = a.extent[0];
+        const uint32_t q0 = fdiv(e0, a.div[0]);
+        const uint32_t r0 = e0 - q0 * ext0;
+        long long row[3][NIN];
+        run_row_offsets<NIN>(a, q0, row[0]);
+        if (r0 + (kRun - 1) >= ext0) {  // the run crosses into the next row(s): rare when rows are long
+            run_row_offsets<NIN>(a, q0 + 1, row[1]);
+            if (ext0 == 2) {
+                run_row_offsets<NIN>(a, q0 + 2, row[2]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NIN; i++) row[2][i] = row[1][i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NIN; i++) row[1][i] = row[2][i] = row[0][i];
         }
 #pragma unroll
-        for (int i = 0; i < NIN; i++) off[i] += (long long)idx[d] * a.stride[i][d];
-        if (last) break;
-    }
-    float v[kRun][NIN];
+        for (int j = 0; j < kRun; j++) {
+            uint32_t r = r0 + j;
+            int c = 0;
+            if (r >= ext0) r -= ext0, c = 1;
+            if (r >= ext0) r -= ext0, c = 2;
+            if (e0 + j < a.n_items) {
 #pragma unroll
-    for (int j = 0; j < kRun; j++) {
-        if (e0 + j < a.n_items) {
-#pragma unroll
-            for (int i = 0; i < NIN; i++) v[j][i] = __ldg(a.in[i] + off[i]);
-            // step to the next logical element: bump the inner axis, carry while an axis wraps
-#pragma unroll
-            for (int d = 0; d < kMaxDims; d++) {
-                idx[d]++;
-#pragma unroll
-                for (int i = 0; i < NIN; i++) off[i] += a.stride[i][d];
-                if (d == a.ndim - 1 || idx[d] < a.extent[d]) break;
-                idx[d] = 0;
-#pragma unroll
-                for (int i = 0; i < NIN; i++) off[i] -= (long long)a.extent[d] * a.stride[i][d];
+                for (int i = 0; i < NIN; i++) {
+                    if (a.mode[i] == 2) {
+                        const long long base = c == 0 ? row[0][i] : (c == 1 ? row[1][i] : row[2][i]);
+                        v[j][i] = __ldg(a.in[i] + base + (long long)r * a.stride[i][0]);
+                    }
+                }
             }
         }
     }
@@ -305,7 +361,7 @@ __global__ void __launch_bounds__(kEwThreads) ew_run_kernel(const NdArgs<F::NIN>
 #pragma unroll
     for (int j = 0; j < kRun; j++) r[j] = (e0 + j < a.n_items) ? f(v[j]) : 0.0f;
     float* dst = a.out + e0;
-    if (a.out_aligned && e0 + kRun <= a.n_items) {
+    if (full) {
         const float4 r4 = make_float4(r[0], r[1], r[2], r[3]);
         if (a.stream_store) __stcs(reinterpret_cast<float4*>(dst), r4);
         else *reinterpret_cast<float4*>(dst) = r4;
@@ -865,6 +921,30 @@ static bool launch_nd_one(const F& f, const Folded& fo, const float* const* in, 
         ew_nd_kernel<1, kUnroll, F><<<blocks, kEwThreads, 0, s>>>(a, f);
     } else {
         a.out_aligned = (uintptr_t)out % 16 == 0;
+        for (int i = 0; i < NIN; i++) {
+            // the run of axes [d1, d2) over which the operand is unit-stride-contiguous; stride 0 everywhere else?
+            int d1 = 0;
+            while (d1 < fo.ndim && fo.in_stride[i][d1] == 0) d1++;
+            uint64_t inner = 1, len = 1;
+            for (int d = 0; d < d1; d++) inner *= fo.extent[d];
+            bool block = true;
+            int d2 = d1;
+            int64_t run = 1;
+            while (d2 < fo.ndim && fo.in_stride[i][d2] == run) {
+                run *= (int64_t)fo.extent[d2];
+                len *= fo.extent[d2];
+                d2++;
+            }
+            for (int d = d2; d < fo.ndim; d++) block = block && fo.in_stride[i][d] == 0;
+            if (d1 == fo.ndim) inner = 1, len = 1;  // a single element broadcast everywhere
+            block = block && inner < (1ull << 31) && len < (1ull << 31);
+            const bool congruent = block && d1 == 0 && d2 == fo.ndim;
+            a.mode[i] = !block ? 2 : (congruent && (uintptr_t)in[i] % 16 == 0 ? 0 : 1);
+            a.blk_inner[i] = (uint32_t)(block ? inner : 1);
+            a.blk_len[i] = (uint32_t)(block ? len : 1);
+            a.blk_inner_div[i] = make_fastdiv(a.blk_inner[i]);
+            a.blk_len_div[i] = make_fastdiv(a.blk_len[i]);
+        }
         const uint64_t threads = (n_items + kRun - 1) / kRun;
         ew_run_kernel<F><<<(unsigned)((threads + kEwThreads - 1) / kEwThreads), kEwThreads, 0, s>>>(a, f);
     }

@@ -14,7 +14,9 @@
 //   reduce_rows_packed  dense [N, 2..8] rows: four rows per thread as aligned 128-bit loads.
 //   reduce_window  overlapping as_strided windows (kept stride == reduced stride == 1): persistent CTAs
 //                  stage a tile + halo in shared memory and form all window sums from per-block
-//                  prefix/suffix scans (half-block lanes for w = 8/16/32/64). Config C5a.
+//                  prefix/suffix scans (half-block lanes for w = 8/16/32/64, config C5a; segmented
+//                  scans over 32-element lane chunks for any other w up to 1024).
+//   reduce_inner_peel  unit-stride rows that are not 16-byte aligned: masked aligned float4 loads.
 //   reduce_sequential  verification mode: the reference's own summation order, one thread per output.
 //   reduce_finish  second pass when the reduced range was split across CTAs (long reduced
 //                  extent, few outputs): combines the per-split partials in a fixed order.
@@ -260,6 +262,79 @@ __global__ void __launch_bounds__(256) reduce_inner_kernel(const RedArgs a) {
     }
 }
 
+// The same for unit-stride rows that are NOT 16-byte aligned (odd row lengths such as 255 or 85, sliced
+// views): every row is read as the aligned float4s that cover it, and the up-to-3 foreign elements in the
+// first and last vector are replaced by the identity. The alignment is resolved per row on the device,
+// so there is no constraint on any stride. (The over-read stays inside the 16-byte chunk that holds a
+// row element, hence inside the allocation.) Scalar lanes left 2^20 rows of 255 floats at 3.7 TB/s.
+template <int OP>
+__device__ __forceinline__ float4 peel_mask(float4 x, int first, int e0) {
+    const float id = rident<OP>();
+    if (first < 0 || first + 3 >= e0) {
+        if (first < 0 || first >= e0) x.x = id;
+        if (first + 1 < 0 || first + 1 >= e0) x.y = id;
+        if (first + 2 < 0 || first + 2 >= e0) x.z = id;
+        if (first + 3 < 0 || first + 3 >= e0) x.w = id;
+    }
+    return x;
+}
+template <int OP, int TEAM>
+__global__ void __launch_bounds__(256) reduce_inner_peel_kernel(const RedArgs a) {
+    const uint32_t gt = (uint32_t)(((uint64_t)blockIdx.x * 256u + threadIdx.x) / TEAM);
+    const uint32_t lane = threadIdx.x % TEAM;
+    const bool live = gt < a.nout;
+    Acc<4> acc = acc_ident<OP, 4>();
+    if (live) {
+        const float* base = a.src + (a.nk ? kept_offset(a, gt) : 0);
+        const int e0 = (int)a.rext[0];
+        const uint32_t n_outer = a.nr_items / a.rext[0];
+        for (uint32_t ro = 0; ro < n_outer; ro++) {
+            long long obase = 0;
+            uint32_t rem = ro;
+            for (int d = 1; d < a.nr; d++) {
+                uint32_t idx;
+                if (d == a.nr - 1) {
+                    idx = rem;
+                } else {
+                    const uint32_t q = fdiv(rem, a.rdiv[d]);
+                    idx = rem - q * a.rext[d];
+                    rem = q;
+                }
+                obase += (long long)idx * a.rstride[d];
+            }
+            const float* row = base + obase;
+            const int m = (int)((reinterpret_cast<uintptr_t>(row) >> 2) & 3);
+            const float4* q = reinterpret_cast<const float4*>(row - m);
+            const uint32_t nvec = (uint32_t)(m + e0 + 3) >> 2;  // vector j holds row elements 4j-m .. 4j-m+3
+            uint32_t j = lane;
+            for (; j + 3 * TEAM < nvec; j += 4 * TEAM) {
+                Acc<4> x0, x1, x2, x3;
+                x0.v = __ldcs(q + j);
+                x1.v = __ldcs(q + j + TEAM);
+                x2.v = __ldcs(q + j + 2 * TEAM);
+                x3.v = __ldcs(q + j + 3 * TEAM);
+                x0.v = peel_mask<OP>(x0.v, 4 * (int)j - m, e0);
+                x1.v = peel_mask<OP>(x1.v, 4 * (int)(j + TEAM) - m, e0);
+                x2.v = peel_mask<OP>(x2.v, 4 * (int)(j + 2 * TEAM) - m, e0);
+                x3.v = peel_mask<OP>(x3.v, 4 * (int)(j + 3 * TEAM) - m, e0);
+                acc_into<OP, 4>(x0, x1);
+                acc_into<OP, 4>(x2, x3);
+                acc_into<OP, 4>(x0, x2);
+                acc_into<OP, 4>(acc, x0);
+            }
+            for (; j < nvec; j += TEAM) {
+                Acc<4> x;
+                x.v = peel_mask<OP>(__ldcs(q + j), 4 * (int)j - m, e0);
+                acc_into<OP, 4>(acc, x);
+            }
+        }
+    }
+    float v = acc_collapse<OP, 4>(acc);
+#pragma unroll
+    for (int o = TEAM / 2; o > 0; o >>= 1) v = racc<OP>(v, __shfl_down_sync(0xffffffffu, v, o, TEAM));
+    if (live && lane == 0) a.dst[gt] = a.finalize ? rfinal<OP>(a.init, v) : v;
+}
+
 // Packed short rows: source is a dense [nout, R] block (R = 2..8) reduced over its inner axis -- the
 // component axis of RGB / xyz / complex data. One lane per output would issue R scalar loads at a stride
 // of R floats; instead a thread takes FOUR rows = 4R consecutive floats = R aligned float4 loads, sums
@@ -392,7 +467,6 @@ reduce_finish_kernel(const float* __restrict__ partial, float* __restrict__ out,
 
 // Fixed-w variant (w = 8/16/32/64): the first half of the CTA's warps build the suffix scans, the
 // second half the prefix scans, each thread owning 64/W blocks held in registers.
-constexpr int kWinThreads = 256;      // generic-w kernel
 constexpr int kWinFixedThreads = 128; // fixed-w kernel: 128 threads x 32 elements = 4096-element span,
 constexpr int kWinLoads = 32;         // all 32 loads of a thread in flight at once; ~5 CTAs per SM
 
@@ -623,61 +697,146 @@ reduce_window_half_kernel(const float* __restrict__ x, float* __restrict__ out, 
     }
 }
 
-// Any-w variant: one thread scans one block serially.
+// Any-w variant (w not in {8,16,32,64}): the same prefix/suffix decomposition, but the block length is a
+// run-time value, so blocks cannot be dealt out to lanes. Instead every lane owns 32 CONSECUTIVE staged
+// elements and the two scans become SEGMENTED scans over the tile (segments = blocks of w):
+//   1. a lane folds its chunk into two aggregates (the open segment at its right end / at its left end),
+//   2. a segmented scan of the aggregates across the CTA (warp shuffles + one shared hop) gives every
+//      lane the value carried into its chunk from the left and from the right,
+//   3. the lane re-walks its chunk seeded with the carries and stores P and S,
+//   4. outputs: S[i] (+) P[i + w - 1] as before.
+// Elements are stored with one pad float per 32 so that lane t's chunk starts at bank t. Tiles start on
+// a block boundary, so the positions of the block boundaries inside a lane's chunk depend on (lane, w)
+// only and are kept as two 32-bit masks. The old kernel (one lane scans one whole block serially) ran a
+// 100-wide window at 1.8 TB/s because only nblk of its 256 lanes had work during the scans.
+constexpr int kAnyT = 128, kAnyL = 32, kAnySpan = kAnyT * kAnyL, kAnyPadded = kAnySpan + kAnySpan / 32;
+
 template <int OP>
-__global__ void __launch_bounds__(kWinThreads)
-reduce_window_kernel(const float* __restrict__ x, float* __restrict__ out, uint32_t nout, uint32_t w, uint32_t nblk,
-                     float init) {
+__global__ void __launch_bounds__(kAnyT, 4)
+reduce_window_any_kernel(const float* __restrict__ x, float* __restrict__ out, uint32_t nout, uint32_t w, uint32_t n_tiles,
+                         uint32_t tiles_per_row, long long row_stride, float init, int init_is_identity) {
     extern __shared__ float wsm[];
-    const uint32_t pitch = w + 1;
-    float* P = wsm;                               // [nblk+1][pitch] prefix scans
-    float* S = wsm + (size_t)(nblk + 1) * pitch;  // [nblk+1][pitch] suffix scans
-    const uint32_t tile = nblk * w;               // outputs per CTA
-    const size_t i0 = (size_t)blockIdx.x * tile;
+    constexpr int T = kAnyT, L = kAnyL, SPAN = kAnySpan, NW = kAnyT / 32;
+    float* P = wsm;               // staged elements, overwritten in place by the prefix scans
+    float* S = wsm + kAnyPadded;  // suffix scans
+    __shared__ float inc[2][T];   // inclusive cross-lane scan values: [0] left-to-right, [1] right-to-left
+    __shared__ float wtot[2][NW];
+    __shared__ int wflag[2][NW];
+    const uint32_t TILE = SPAN - (w - 1);  // outputs per tile
     const size_t n_in = (size_t)nout + w - 1;
-    const uint32_t span = tile + w;
-    // stage with 8 loads in flight per thread (the loop-carried div/mod otherwise serialises them)
-    for (uint32_t e0 = 0; e0 < span; e0 += 8 * kWinThreads) {
-        float v[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const uint32_t e = e0 + u * kWinThreads + threadIdx.x;
-            const size_t gi = i0 + e;
-            v[u] = (e < span && gi < n_in) ? __ldcs(x + gi) : rident<OP>();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool ident = init_is_identity != 0;
+    const float id = rident<OP>();
+    uint32_t starts = 0, ends = 0;  // bit k: chunk element k opens / closes a block
+    {
+        uint32_t pos = (uint32_t)(tid * L) % w;
+        for (int k = 0; k < L; k++) {
+            if (pos == 0) starts |= 1u << k;
+            if (pos == w - 1) ends |= 1u << k;
+            if (++pos == w) pos = 0;
         }
+    }
+    const uint32_t k_first = (uint32_t)tid % w, k_step = (uint32_t)T % w;
+
+    float v[L];
+    auto fetch = [&](uint32_t tile) {
+        const uint32_t row = tile / tiles_per_row;
+        const size_t i0 = (size_t)(tile - row * tiles_per_row) * TILE;
+        const float* src = x + (long long)row * row_stride + i0 + tid;
+        if (i0 + SPAN <= n_in) {
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const uint32_t e = e0 + u * kWinThreads + threadIdx.x;
-            if (e < span) {
-                const uint32_t b = e / w, k = e - b * w;
-                P[b * pitch + k] = v[u];
+            for (int u = 0; u < L; u++) v[u] = __ldcs(src + u * T);
+        } else {
+#pragma unroll
+            for (int u = 0; u < L; u++) v[u] = (i0 + u * T + tid < n_in) ? __ldcs(src + u * T) : id;
+        }
+    };
+    uint32_t tile = blockIdx.x;
+    if (tile < n_tiles) fetch(tile);
+    for (; tile < n_tiles; tile += gridDim.x) {
+        // element e = u*T + tid lives at e + e/32 = u*(T + NW) + tid + warp
+#pragma unroll
+        for (int u = 0; u < L; u++) P[u * (T + NW) + tid + warp] = v[u];
+        __syncthreads();
+        if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);
+        float xr[L];
+        float* const mine = P + tid * (L + 1);
+#pragma unroll
+        for (int k = 0; k < L; k++) xr[k] = mine[k];
+        // 1. aggregates: al = fold of the elements after the last block start (all of them if none),
+        //                ar = fold of the elements before the first block end (all of them if none)
+        float al = xr[0], ar = xr[L - 1];
+#pragma unroll
+        for (int k = 1; k < L; k++) {
+            al = ((starts >> k) & 1u) ? xr[k] : racc<OP>(al, xr[k]);
+            ar = ((ends >> (L - 1 - k)) & 1u) ? xr[L - 1 - k] : racc<OP>(xr[L - 1 - k], ar);
+        }
+        // 2. segmented inclusive scans of (aggregate, "chunk holds a boundary") across the CTA
+        float sl = al, sr = ar;
+        int fl = starts != 0, fr = ends != 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const float ol = __shfl_up_sync(0xffffffffu, sl, d), orr = __shfl_down_sync(0xffffffffu, sr, d);
+            const int ofl = __shfl_up_sync(0xffffffffu, fl, d), ofr = __shfl_down_sync(0xffffffffu, fr, d);
+            if (lane >= d) {
+                if (!fl) sl = racc<OP>(ol, sl);
+                fl |= ofl;
+            }
+            if (lane + d < 32) {
+                if (!fr) sr = racc<OP>(sr, orr);
+                fr |= ofr;
             }
         }
-    }
-    __syncthreads();
-    for (uint32_t b = threadIdx.x; b <= nblk; b += kWinThreads) {
-        float* p = P + b * pitch;
-        float* s = S + b * pitch;
-        float run = p[w - 1];
-        s[w - 1] = run;
-        for (int k = (int)w - 2; k >= 0; k--) {
-            run = racc<OP>(p[k], run);
-            s[k] = run;
+        if (lane == 31) wtot[0][warp] = sl, wflag[0][warp] = fl;
+        if (lane == 0) wtot[1][warp] = sr, wflag[1][warp] = fr;
+        __syncthreads();
+        if (!fl && warp > 0) {  // still open towards the left: take what the warps before this one carry
+            float c = wtot[0][0];
+            for (int j = 1; j < warp; j++) c = wflag[0][j] ? wtot[0][j] : racc<OP>(c, wtot[0][j]);
+            sl = racc<OP>(c, sl);
         }
-        run = p[0];
-        for (uint32_t k = 1; k < w; k++) {
-            run = racc<OP>(run, p[k]);
-            p[k] = run;
+        if (!fr && warp < NW - 1) {
+            float c = wtot[1][NW - 1];
+            for (int j = NW - 2; j > warp; j--) c = wflag[1][j] ? wtot[1][j] : racc<OP>(wtot[1][j], c);
+            sr = racc<OP>(sr, c);
         }
-    }
-    __syncthreads();
-    for (uint32_t e = threadIdx.x; e < tile; e += kWinThreads) {
-        const size_t gi = i0 + e;
-        if (gi >= nout) break;
-        const uint32_t b = e / w, k = e - b * w;
-        float v = S[b * pitch + k];
-        if (k) v = racc<OP>(v, P[(b + 1) * pitch + k - 1]);
-        __stcs(out + gi, rfinal<OP>(init, v));
+        inc[0][tid] = sl;
+        inc[1][tid] = sr;
+        __syncthreads();
+        // 3. the scans proper, seeded with the carries (lane 0 starts a block; the carry into the last
+        //    lane from beyond the tile does not exist, and the S values that would need it are never read)
+        float runp = tid > 0 ? inc[0][tid - 1] : id;
+        float runs = tid < T - 1 ? inc[1][tid + 1] : id;
+        float* const sfx = S + tid * (L + 1);
+#pragma unroll
+        for (int k = 0; k < L; k++) {
+            runp = ((starts >> k) & 1u) ? xr[k] : racc<OP>(runp, xr[k]);
+            mine[k] = runp;
+            const int kr = L - 1 - k;
+            runs = ((ends >> kr) & 1u) ? xr[kr] : racc<OP>(xr[kr], runs);
+            sfx[kr] = runs;
+        }
+        __syncthreads();
+        // 4. output e = u*T + tid (k = e % w): S[e] (+) P[e + w - 1] unless the window is exactly one block
+        const uint32_t row = tile / tiles_per_row;
+        const size_t i0 = (size_t)(tile - row * tiles_per_row) * TILE;
+        float* dst = out + (size_t)row * nout + i0 + tid;
+        uint32_t kpos = k_first;
+#pragma unroll 8
+        for (int u = 0; u < L; u++) {
+            const uint32_t e = u * T + tid;
+            if (e < TILE && i0 + e < nout) {
+                float r = S[e + (e >> 5)];
+                if (kpos != 0) {
+                    const uint32_t e2 = e + w - 1;
+                    r = racc<OP>(r, P[e2 + (e2 >> 5)]);
+                }
+                __stcs(dst + u * T, rfinal_fast<OP>(init, r, ident));
+            }
+            kpos += k_step;
+            if (kpos >= w) kpos -= w;
+        }
+        __syncthreads();
     }
 }
 
@@ -711,6 +870,24 @@ static bool launch_window_fixed(const float* src, float* out, uint32_t nout, uin
         reduce_window_fixed_kernel<OP, W><<<blocks, kWinFixedThreads, smem, rt().stream>>>(src, out, nout, n_tiles, tiles_per_row, row_stride, init, init_is_identity);
     note_launch("reduce_window");
     return check_launch("reduce_window");
+}
+
+template <int OP>
+static bool launch_window_any(const float* src, float* out, uint32_t nout, uint32_t w, uint32_t rows, long long row_stride, float init) {
+    const float ident_tab[AL_REDOP_COUNT] = {0.0f, -INFINITY, INFINITY, 1.0f};
+    const int init_is_identity = memcmp(&init, &ident_tab[OP], sizeof(float)) == 0;
+    const uint32_t tile = kAnySpan - (w - 1);
+    const unsigned tiles_per_row = (unsigned)(((uint64_t)nout + tile - 1) / tile);
+    const uint64_t all_tiles = (uint64_t)tiles_per_row * rows;
+    if (all_tiles >= (1ull << 31)) return set_error("NotImplementedError: too many window tiles"), false;
+    const unsigned n_tiles = (unsigned)all_tiles;
+    const long per_sm = rt().window_ctas_per_sm > 0 ? rt().window_ctas_per_sm : 32;
+    unsigned blocks = (unsigned)(kNumSMs * per_sm);
+    if (blocks > n_tiles) blocks = n_tiles;
+    const size_t smem = 2ull * kAnyPadded * sizeof(float);
+    reduce_window_any_kernel<OP><<<blocks, kAnyT, smem, rt().stream>>>(src, out, nout, w, n_tiles, tiles_per_row, row_stride, init, init_is_identity);
+    note_launch("reduce_window_any");
+    return check_launch("reduce_window_any");
 }
 
 // ---- host planning ------------------------------------------------------------------------------------
@@ -803,20 +980,8 @@ static bool run_reduce(const float* src, float* out, const AxisList& K, const Ax
             case 16: return launch_window_fixed<OP, 16>(src, out, per_row, rows, row_stride, init);
             case 32: return launch_window_fixed<OP, 32>(src, out, per_row, rows, row_stride, init);
             case 64: return launch_window_fixed<OP, 64>(src, out, per_row, rows, row_stride, init);
-            default: break;
+            default: return launch_window_any<OP>(src, out, per_row, w, rows, row_stride, init);
         }
-    }
-    if (!general && !r.disable_window && win_axes && K.n == 1 && R.extent[0] >= 8 && R.extent[0] <= 1024 && nout >= 4 * R.extent[0]) {
-        const uint32_t w = (uint32_t)R.extent[0];
-        uint32_t nblk = 8192 / w;  // ~8K outputs per CTA
-        if (nblk < 1) nblk = 1;
-        size_t smem = 2ull * (nblk + 1) * (w + 1) * sizeof(float);
-        if (smem > 48 * 1024) cudaFuncSetAttribute(reduce_window_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        const uint32_t tile = nblk * w;
-        unsigned blocks = (unsigned)((nout + tile - 1) / tile);
-        reduce_window_kernel<OP><<<blocks, kWinThreads, smem, st>>>(src, out, (uint32_t)nout, w, nblk, init);
-        note_launch("reduce_window");
-        return check_launch("reduce_window");
     }
 
     // -- dense [nout, R] with a short reduced inner axis --
@@ -952,6 +1117,22 @@ static bool run_reduce(const float* src, float* out, const AxisList& K, const Ax
         if (vec) reduce_inner_cta_kernel<OP, 4><<<grid, 256, 0, st>>>(a);
         else reduce_inner_cta_kernel<OP, 1><<<grid, 256, 0, st>>>(a);
         note_launch("reduce_inner_cta");
+    } else if (!vec && !general && r.reduce_peel && R.n > 0 && R.stride[0] == 1 && R.extent[0] >= 16 && R.extent[0] < (1u << 29)) {
+        // unit-stride rows the aligned 128-bit path cannot take: masked aligned vectors (see the kernel)
+        const uint32_t nvec = (uint32_t)(R.extent[0] / 4 + 1);
+        const uint32_t per_lane = r.reduce_loads_per_lane > 0 ? (uint32_t)r.reduce_loads_per_lane : 4;
+        uint32_t team = pow2_ceil((nvec + per_lane - 1) / per_lane);
+        if (team > 32) team = 32;
+        unsigned gx = (unsigned)(((uint64_t)nout * team + 255) / 256);
+        switch (team) {
+            case 1: reduce_inner_peel_kernel<OP, 1><<<gx, 256, 0, st>>>(a); break;
+            case 2: reduce_inner_peel_kernel<OP, 2><<<gx, 256, 0, st>>>(a); break;
+            case 4: reduce_inner_peel_kernel<OP, 4><<<gx, 256, 0, st>>>(a); break;
+            case 8: reduce_inner_peel_kernel<OP, 8><<<gx, 256, 0, st>>>(a); break;
+            case 16: reduce_inner_peel_kernel<OP, 16><<<gx, 256, 0, st>>>(a); break;
+            default: reduce_inner_peel_kernel<OP, 32><<<gx, 256, 0, st>>>(a); break;
+        }
+        note_launch("reduce_inner_peel");
     } else {
         // lanes per output: ~4 loads per lane for 128-bit loads, ~32 for 4-byte loads (measured: 2^20 rows of
         // 255 floats 3.35 -> 4.48 TB/s; 2^24 rows of 64 floats best at 4), never wider than the inner axis

@@ -383,6 +383,7 @@ int al_set_tuning(const char* key, long value) {
     else if (k == "stream_tma") g_rt.stream_tma = value;
     else if (k == "chain_block") g_rt.chain_block = value;
     else if (k == "peer_collective") g_rt.peer_collective = value;
+    else if (k == "reduce_peel") g_rt.reduce_peel = value;
     else if (k == "outer_tile") g_rt.outer_tile = value;
     else {
         set_error("KeyError: unknown tuning key '%s'", k.c_str());

@@ -301,3 +301,25 @@ def test_errors_raise_instead_of_aborting(al):
         al.apply(lambda v: math.erf(v), a)
     assert not lib.array_op(None, a.buffer)
     assert lib.al_last_error().startswith(b"NotImplementedError")
+
+
+@pytest.mark.parametrize("sa,sb", [((50001, 3), (3,)), ((3,), (50001, 3)), ((50001, 3), (50001, 1)), ((4001, 1, 7), (1, 9, 7)),
+                                   ((1000, 5, 3), (5, 1)), ((333, 3), (333, 3)), ((2, 50001), (2, 1))])
+@pytest.mark.parametrize("op", ["sum", "sub", "div", "max", "lt"])
+def test_odd_inner_extents_congruent_operand_takes_128_bit_loads(al, orc, rng, sa, sb, op):
+    """The 4-outputs-per-thread fallback: an operand laid out exactly like the output is read with one float4
+    per thread, the broadcast operand through stepped scalar loads; also with misaligned operands and outputs
+    whose element count is not a multiple of 4."""
+    a, b = rng.standard_normal(sa).astype(np.float32), rng.standard_normal(sb).astype(np.float32)
+    got = getattr(al, "add" if op == "sum" else op)(al.from_numpy(a), al.from_numpy(b))
+    assert_bit_equal(al.to_numpy(got), orc.binary(op, a, b), f"{op} {sa} {sb}")
+    # the same operands as misaligned views of a padded base (4-byte shifted pointers)
+    pa, pb = np.zeros(a.size + 1, np.float32), np.zeros(b.size + 1, np.float32)
+    pa[1:], pb[1:] = a.reshape(-1), b.reshape(-1)
+    def row_major(shape):
+        return tuple(int(np.prod(shape[i + 1:])) for i in range(len(shape)))
+
+    A = al.from_numpy(pa)[1:a.size + 1].as_strided(shape=sa, stride=row_major(sa))
+    B = al.from_numpy(pb)[1:b.size + 1].as_strided(shape=sb, stride=row_major(sb))
+    got = getattr(al, "add" if op == "sum" else op)(A, B)
+    assert_bit_equal(al.to_numpy(got), orc.binary(op, a, b), f"{op} {sa} {sb} shifted")

@@ -285,3 +285,80 @@ def test_cross_gpu_entry_point_is_the_local_reduce_in_a_single_process(al, orc, 
             got = core._new(lib.al_comm_reduce(REDOPS.index(op), a.buffer, dims_c, n))
             assert_bit_equal(al.to_numpy(got), orc.reduce(op, x, dims))
             assert_bit_equal(al.to_numpy(dist.reduce_sharded(a, op, dims)), orc.reduce(op, x, dims))
+
+
+@pytest.mark.parametrize("rows,n,w", [(4, 9000, 100), (3, 5000, 24), (2, 13000, 1000), (7, 4500, 12)])
+def test_batched_sliding_windows_any_width(al, orc, rng, rows, n, w):
+    """Widths without a dedicated kernel go through the segmented-scan window kernel, batched rows included."""
+    from arraylib_b200._lib import lib
+    base = int_data(rng, (rows, n))
+    V = al.from_numpy(base.reshape(-1)).as_strided(shape=(rows, n - w + 1, w), stride=(n, 1, 1))
+    vn = np.lib.stride_tricks.as_strided(base, shape=(rows, n - w + 1, w), strides=(4 * n, 4, 4))
+    got = al.reduce_sum(V, dims=[2])
+    assert lib.al_last_kernel() == b"reduce_window_any"
+    assert_bit_equal(al.to_numpy(got), orc.reduce("sum", vn, (2,)), "batched windows")
+    assert_bit_equal(al.to_numpy(al.reduce_max(V, dims=[2])), orc.reduce("max", vn, (2,)), "batched windows max")
+    assert_bit_equal(al.to_numpy(al.reduce_min(V, dims=[2])), orc.reduce("min", vn, (2,)), "batched windows min")
+
+
+@pytest.mark.parametrize("w", [11, 31, 48, 100, 257, 777])
+def test_any_width_windows_persistent_tiles_and_nan_stretches(al, orc, rng, w):
+    """Several tiles per CTA (window_ctas_per_sm=1), all-NaN windows, and the generic reduce path as a second opinion."""
+    from arraylib_b200._lib import lib
+    n = 2_000_000
+    base = int_data(rng, (n,))
+    base[5000:5000 + 2 * w] = np.nan
+    V = al.from_numpy(base).as_strided(shape=(n - w + 1, w), stride=(1, 1))
+    vn = np.lib.stride_tricks.as_strided(base, shape=(n - w + 1, w), strides=(4, 4))
+    lib.al_set_tuning(b"window_ctas_per_sm", 1)
+    try:
+        for op in ("sum", "max", "min"):
+            got = al.to_numpy(getattr(al, f"reduce_{op}")(V, dims=[1]))
+            assert lib.al_last_kernel() == b"reduce_window_any"
+            assert_bit_equal(got, orc.reduce(op, vn, (1,)), f"{op} w={w}")
+    finally:
+        lib.al_set_tuning(b"window_ctas_per_sm", 0)
+    f = rng.standard_normal(300000).astype(np.float32)
+    F = al.from_numpy(f).as_strided(shape=(f.size - w + 1, w), stride=(1, 1))
+    fast = al.to_numpy(al.reduce_max(F, dims=[1]))
+    lib.al_set_tuning(b"disable_window", 1)
+    try:
+        slow = al.to_numpy(al.reduce_max(F, dims=[1]))
+    finally:
+        lib.al_set_tuning(b"disable_window", 0)
+    assert_bit_equal(fast, slow, "window vs generic")
+
+
+@pytest.mark.parametrize("shape,dims", [((4096, 255), (1,)), ((3, 2048, 85), (0, 2)), ((3, 2048, 85), (2,)), ((1000, 17), (1,)),
+                                        ((257, 1023), (1,)), ((5, 7, 129), (1, 2)), ((2, 3, 4, 33), (3,)), ((64, 16), (1,))])
+def test_misaligned_rows_use_masked_vectors(al, orc, rng, shape, dims):
+    """Unit-stride reduced rows that are not 16-byte aligned: reduce_inner_peel (aligned float4 loads, foreign
+    elements masked), against the oracle and against the scalar-lane kernel."""
+    from arraylib_b200._lib import lib
+    x = int_data(rng, shape)
+    X = al.from_numpy(x)
+    for op in ("sum", "max", "min"):
+        got = al.to_numpy(getattr(al, f"reduce_{op}")(X, dims=dims))
+        kernel = lib.al_last_kernel()
+        assert_bit_equal(got, orc.reduce(op, x, dims), f"{op} {shape} {dims}")
+    if shape[-1] % 4 and shape[-1] >= 16 and x.size // int(np.prod([shape[d] for d in dims])) > 64:
+        assert kernel == b"reduce_inner_peel", kernel
+    # sliced views: every row starts at a different misalignment; NaN and -0 survive the masking
+    f = rng.standard_normal((300, 270)).astype(np.float32)
+    f[5, 7:30] = np.nan
+    f[9] = -0.0
+    F = al.from_numpy(f)
+    for c0 in (0, 1, 2, 3):
+        for c1 in (270, 269, 258, 257):
+            v, vn = F[2:300, c0:c1], f[2:300, c0:c1]
+            for op in ("max", "min"):
+                assert_bit_equal(al.to_numpy(getattr(al, f"reduce_{op}")(v, dims=(1,))), orc.reduce(op, vn, (1,)), f"{op} cols {c0}:{c1}")
+            lib.al_set_tuning(b"reduce_peel", 0)
+            try:
+                scalar = al.to_numpy(al.reduce_max(v, dims=(1,)))
+            finally:
+                lib.al_set_tuning(b"reduce_peel", 1)
+            assert_bit_equal(al.to_numpy(al.reduce_max(v, dims=(1,))), scalar, "peel vs scalar lanes")
+            err = np.abs(al.to_numpy(al.reduce_sum(v, dims=(1,))).astype(np.float64) - np.nansum(vn.astype(np.float64), axis=1, keepdims=True))
+            ok = np.isnan(orc.reduce("sum", vn, (1,))) | (err <= 2 * vn.shape[1] * 2.0**-24 * np.nansum(np.abs(vn), axis=1, keepdims=True) + 1e-30)
+            assert np.all(ok)
