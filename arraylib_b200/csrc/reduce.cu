@@ -703,8 +703,10 @@ reduce_window_half_kernel(const float* __restrict__ x, float* __restrict__ out, 
 //   1. a lane folds its chunk into two aggregates (the open segment at its right end / at its left end),
 //   2. a segmented scan of the aggregates across the CTA (warp shuffles + one shared hop) gives every
 //      lane the value carried into its chunk from the left and from the right,
-//   3. the lane re-walks its chunk seeded with the carries and stores P and S,
-//   4. outputs: S[i] (+) P[i + w - 1] as before.
+//   3. the lane re-walks its chunk seeded with the carries and stores S (inclusive) and P (EXCLUSIVE:
+//      what precedes the element inside its block, the identity at a block start),
+//   4. outputs: S[i] (+) P[i + w] -- no special case for windows that coincide with a block, and both
+//      shared addresses are a per-lane base plus a compile-time offset.
 // Elements are stored with one pad float per 32 so that lane t's chunk starts at bank t. Tiles start on
 // a block boundary, so the positions of the block boundaries inside a lane's chunk depend on (lane, w)
 // only and are kept as two 32-bit masks. The old kernel (one lane scans one whole block serially) ran a
@@ -722,7 +724,7 @@ reduce_window_any_kernel(const float* __restrict__ x, float* __restrict__ out, u
     __shared__ float inc[2][T];   // inclusive cross-lane scan values: [0] left-to-right, [1] right-to-left
     __shared__ float wtot[2][NW];
     __shared__ int wflag[2][NW];
-    const uint32_t TILE = SPAN - (w - 1);  // outputs per tile
+    const uint32_t TILE = SPAN - w;  // outputs per tile
     const size_t n_in = (size_t)nout + w - 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool ident = init_is_identity != 0;
@@ -736,7 +738,9 @@ reduce_window_any_kernel(const float* __restrict__ x, float* __restrict__ out, u
             if (++pos == w) pos = 0;
         }
     }
-    const uint32_t k_first = (uint32_t)tid % w, k_step = (uint32_t)T % w;
+    // output e = u*T + tid reads S at e + e/32 = u*(T + NW) + tid + warp and P at the padded index of e + w
+    const float* const s_lane = S + tid + warp;
+    const float* const p_lane = P + (tid + w) + ((tid + w) >> 5);
 
     float v[L];
     auto fetch = [&](uint32_t tile) {
@@ -810,31 +814,26 @@ reduce_window_any_kernel(const float* __restrict__ x, float* __restrict__ out, u
         float* const sfx = S + tid * (L + 1);
 #pragma unroll
         for (int k = 0; k < L; k++) {
-            runp = ((starts >> k) & 1u) ? xr[k] : racc<OP>(runp, xr[k]);
-            mine[k] = runp;
+            const float before = ((starts >> k) & 1u) ? id : runp;  // exclusive prefix of element k
+            mine[k] = before;
+            runp = racc<OP>(before, xr[k]);
             const int kr = L - 1 - k;
-            runs = ((ends >> kr) & 1u) ? xr[kr] : racc<OP>(xr[kr], runs);
+            const float after = ((ends >> kr) & 1u) ? id : runs;
+            runs = racc<OP>(xr[kr], after);
             sfx[kr] = runs;
         }
         __syncthreads();
-        // 4. output e = u*T + tid (k = e % w): S[e] (+) P[e + w - 1] unless the window is exactly one block
+        // 4. output e = u*T + tid: S[e] (+) Pex[e + w]
         const uint32_t row = tile / tiles_per_row;
         const size_t i0 = (size_t)(tile - row * tiles_per_row) * TILE;
         float* dst = out + (size_t)row * nout + i0 + tid;
-        uint32_t kpos = k_first;
-#pragma unroll 8
+        const uint32_t live = (uint32_t)min((size_t)TILE, (size_t)nout - i0);  // outputs of this tile that exist
+#pragma unroll
         for (int u = 0; u < L; u++) {
-            const uint32_t e = u * T + tid;
-            if (e < TILE && i0 + e < nout) {
-                float r = S[e + (e >> 5)];
-                if (kpos != 0) {
-                    const uint32_t e2 = e + w - 1;
-                    r = racc<OP>(r, P[e2 + (e2 >> 5)]);
-                }
+            if (u * T + tid < live) {
+                const float r = racc<OP>(s_lane[u * (T + NW)], p_lane[u * (T + NW)]);
                 __stcs(dst + u * T, rfinal_fast<OP>(init, r, ident));
             }
-            kpos += k_step;
-            if (kpos >= w) kpos -= w;
         }
         __syncthreads();
     }
@@ -876,7 +875,7 @@ template <int OP>
 static bool launch_window_any(const float* src, float* out, uint32_t nout, uint32_t w, uint32_t rows, long long row_stride, float init) {
     const float ident_tab[AL_REDOP_COUNT] = {0.0f, -INFINITY, INFINITY, 1.0f};
     const int init_is_identity = memcmp(&init, &ident_tab[OP], sizeof(float)) == 0;
-    const uint32_t tile = kAnySpan - (w - 1);
+    const uint32_t tile = kAnySpan - w;
     const unsigned tiles_per_row = (unsigned)(((uint64_t)nout + tile - 1) / tile);
     const uint64_t all_tiles = (uint64_t)tiles_per_row * rows;
     if (all_tiles >= (1ull << 31)) return set_error("NotImplementedError: too many window tiles"), false;
