@@ -119,6 +119,7 @@ def _load():
     sig("al_comm_init", C.c_int, C.c_char_p, C.c_int, C.c_int)
     sig("al_comm_allreduce", C.c_int, ArrayP, C.c_int)
     sig("al_comm_allgather", C.c_int, ArrayP, ArrayP)
+    sig("al_comm_alltoall", C.c_int, ArrayP, ArrayP)
     sig("al_comm_reduce", ArrayP, C.c_int, ArrayP, SizeP, C.c_size_t)
     sig("al_comm_transport", C.c_char_p)
     sig("al_comm_destroy", C.c_int)

@@ -120,6 +120,9 @@ bool launch_strided_assign(float* dst, const Folded& f, const float* src, float 
 NDArray* reduce_impl(int redop, const NDArray* src, const size_t* dims, size_t ndims, float init,
                      bool custom_init);
 
+// ---- multi-GPU (comm.cu) -----------------------------------------------------------------------
+bool comm_error_pending();  // true (error set) once a peer-memory collective has timed out
+
 // ---- fills (runtime.cu) ------------------------------------------------------------------------
 bool fill_const(float* p, size_t n, float v);
 

@@ -19,6 +19,10 @@ struct Nccl {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 static Nccl g_nccl;
@@ -46,6 +50,10 @@ static bool load_nccl() {
     AL_SYM(CommDestroy, "ncclCommDestroy")
     AL_SYM(AllReduce, "ncclAllReduce")
     AL_SYM(AllGather, "ncclAllGather")
+    AL_SYM(Send, "ncclSend")
+    AL_SYM(Recv, "ncclRecv")
+    AL_SYM(GroupStart, "ncclGroupStart")
+    AL_SYM(GroupEnd, "ncclGroupEnd")
     AL_SYM(GetErrorString, "ncclGetErrorString")
 #undef AL_SYM
     return true;
@@ -305,6 +313,8 @@ static bool peer_error_raised() {
     return false;
 }
 
+bool comm_error_pending() { return peer_error_raised(); }
+
 bool peer_available() {
     return g_nccl.comm && g_nccl.world > 1 && rt().peer_collective && (!g_peer.tried || g_peer.ok);
 }
@@ -403,7 +413,14 @@ int al_comm_allreduce(NDArray* a, int redop) {
     if (!is_contiguous(a)) return set_error("ValueError: allreduce needs a contiguous array"), -1;
     const ncclRedOp_t ops[AL_REDOP_COUNT] = {ncclSum, ncclMax, ncclMin, ncclProd};
     if (redop < 0 || redop >= AL_REDOP_COUNT) return set_error("ValueError: unknown reduce op %d", redop), -1;
+    if (peer_error_raised()) return -1;
     size_t n = count_of(a->lay->shape, a->lay->ndim);
+    PeerMap map;
+    if (peer_begin(n, &map)) {  // same windows as al_comm_reduce: push, rank-ordered combine, collect (in place)
+        const float ident[AL_REDOP_COUNT] = {0.0f, -INFINITY, INFINITY, 1.0f};
+        return peer_push(a->ptr, n, map) && peer_finish(redop, a->ptr, n, ident[redop]) ? 0 : -1;
+    }
+    clear_error();
     if (!nccl_ok(g_nccl.AllReduce(a->ptr, a->ptr, n, ncclFloat32, ops[redop], g_nccl.comm, rt().stream), "ncclAllReduce"))
         return -1;
     note_launch("nccl_allreduce");
@@ -420,6 +437,27 @@ int al_comm_allgather(const NDArray* shard, NDArray* full) {
         return set_error("ValueError: allgather output must hold world * shard elements"), -1;
     if (!nccl_ok(g_nccl.AllGather(shard->ptr, full->ptr, n, ncclFloat32, g_nccl.comm, rt().stream), "ncclAllGather")) return -1;
     note_launch("nccl_allgather");
+    return 0;
+}
+
+int al_comm_alltoall(const NDArray* send, NDArray* recv) {
+    AL_ENTER;
+    if (!valid(send, "al_comm_alltoall") || !valid(recv, "al_comm_alltoall")) return -1;
+    if (!g_nccl.comm) return set_error("RuntimeError: al_comm_init has not been called"), -1;
+    if (!is_contiguous(send) || !is_contiguous(recv)) return set_error("ValueError: alltoall needs contiguous arrays"), -1;
+    const size_t n = count_of(send->lay->shape, send->lay->ndim);
+    const size_t world = (size_t)g_nccl.world;
+    if (count_of(recv->lay->shape, recv->lay->ndim) != n || n % world != 0)
+        return set_error("ValueError: alltoall needs equal-sized arrays whose element count is a multiple of the world size"), -1;
+    const size_t chunk = n / world;
+    // block r of `send` goes to rank r; block r of `recv` comes from rank r (grouped point-to-point, one NCCL launch)
+    bool ok = nccl_ok(g_nccl.GroupStart(), "ncclGroupStart");
+    for (size_t r = 0; ok && r < world; r++) {
+        ok = nccl_ok(g_nccl.Send(send->ptr + r * chunk, chunk, ncclFloat32, (int)r, g_nccl.comm, rt().stream), "ncclSend") &&
+             nccl_ok(g_nccl.Recv(recv->ptr + r * chunk, chunk, ncclFloat32, (int)r, g_nccl.comm, rt().stream), "ncclRecv");
+    }
+    if (!nccl_ok(g_nccl.GroupEnd(), "ncclGroupEnd") || !ok) return -1;
+    note_launch("nccl_alltoall");
     return 0;
 }
 

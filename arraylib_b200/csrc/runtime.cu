@@ -296,6 +296,7 @@ int al_sync(void) {
               cuda_ok(cudaStreamSynchronize(g_rt.stream), "cudaStreamSynchronize") &&
               cuda_ok(cudaStreamSynchronize(g_rt.d2h_stream), "cudaStreamSynchronize(d2h)");
     drain_pending_downloads();
+    if (ok && comm_error_pending()) ok = false;  // a peer-memory collective gave up waiting for another rank
     return ok ? 0 : -1;
 }
 

@@ -151,6 +151,66 @@ def allgather(shard):
     return full
 
 
+def allgather_ragged(shard, total_rows: int):
+    """allgather for leading-axis blocks of unequal height (shard_bounds): pad to the tallest block, gather,
+    drop the padding."""
+    from . import core
+
+    world = _state["world"]
+    if world == 1:
+        return shard
+    if total_rows % world == 0:
+        return allgather(shard)
+    rest = tuple(shard.shape[1:])
+    tallest = -(-total_rows // world)
+    padded = core.zeros((tallest,) + rest)
+    padded[tuple([slice(0, shard.shape[0])] + [slice(0, e) for e in rest])] = shard
+    stacked = allgather(padded)
+    blocks = []
+    for r in range(world):
+        lo, hi = shard_bounds(total_rows, r, world)
+        if hi > lo:
+            blocks.append(stacked[tuple([slice(r * tallest, r * tallest + hi - lo)] + [slice(0, e) for e in rest])])
+    return blocks[0] if len(blocks) == 1 else core.cat(blocks, [0])
+
+
+def alltoall(send):
+    """Block r (of `world` equal blocks of the flattened array) goes to rank r; returns the received blocks."""
+    from . import core
+    from ._lib import check_rc, lib
+
+    src = send if send.stride == tuple(_row_major(send.shape)) else core.copy(send, deep=True)
+    recv = core.zeros(src.shape)
+    check_rc(lib.al_comm_alltoall(src.buffer, recv.buffer))
+    return recv
+
+
+def reshard_plan(global_shape, perm, world: int) -> dict:
+    """How transpose(perm) of a leading-axis-sharded array is carried out (pure planning, CPU-testable).
+    `local`: axis 0 stays in front, every rank permutes its own block. `alltoall`: the new leading axis is cut
+    into `world` blocks, block j of every rank's transposed piece travels to rank j, and the pieces are
+    interleaved along `q`, the new position of the old leading axis. `gather`: extents do not divide evenly;
+    replicate, transpose, keep the own block."""
+    perm = tuple(perm)
+    assert sorted(perm) == list(range(len(global_shape))), "perm must be a permutation of the axes"
+    new_shape = tuple(global_shape[p] for p in perm)
+    if perm[0] == 0 or world == 1:
+        return {"how": "local", "shape": new_shape}
+    if global_shape[0] % world or new_shape[0] % world:
+        return {"how": "gather", "shape": new_shape}
+    q = perm.index(0)
+    rows, lead = global_shape[0] // world, new_shape[0] // world
+    a = 1
+    for e in new_shape[1:q]:
+        a *= e
+    b = 1
+    for e in new_shape[q + 1:]:
+        b *= e
+    return {"how": "alltoall", "shape": new_shape, "q": q, "rows": rows, "lead": lead,
+            "recv_view": (world, lead, a, rows, b), "interleave": (1, 2, 0, 3, 4),
+            "local_shape": (lead,) + new_shape[1:q] + (rows * world,) + new_shape[q + 1:]}
+
+
 def _row_major(shape):
     out, run = [], 1
     for e in reversed(shape):
@@ -235,13 +295,33 @@ class ShardedArray:
     def reduce_max(self, *, dims=None): return self._reduce("max", dims)
     def reduce_min(self, *, dims=None): return self._reduce("min", dims)
 
+    # -- re-sharding ---------------------------------------------------------------------------------
+    def transpose(self, perm):
+        """transpose(perm) of the GLOBAL array; the result is sharded along its new leading axis. Local when
+        axis 0 stays in front, otherwise one all-to-all (see reshard_plan)."""
+        from . import core
+        world, me = _state["world"], _state["rank"]
+        if self.placement == "replicated":
+            return ShardedArray(core.transpose(self.local, perm), tuple(self.shape[p] for p in perm), "replicated")
+        plan = reshard_plan(self.shape, perm, world)
+        if plan["how"] == "local":
+            return ShardedArray(core.transpose(self.local, perm), plan["shape"], "sharded")
+        if plan["how"] == "gather":
+            whole = core.transpose(allgather_ragged(self.local, self.shape[0]), perm)
+            lo, hi = shard_bounds(plan["shape"][0], me, world)
+            sl = tuple([slice(lo, hi)] + [slice(0, e) for e in plan["shape"][1:]])
+            return ShardedArray(core.copy(whole[sl], deep=True), plan["shape"], "sharded")
+        piece = core.copy(core.transpose(self.local, perm), deep=True)   # (new leading axis in full, ..., own rows at q, ...)
+        got = alltoall(piece)                                              # block i = rank i's rows of MY leading block
+        mixed = core.transpose(core.reshape(got, plan["recv_view"]), plan["interleave"])
+        return ShardedArray(core.reshape(mixed, plan["local_shape"]), plan["shape"], "sharded")
+
     # -- materialisation ----------------------------------------------------------------------------
     def gather(self):
-        """The full array on every rank (allgather; needs equal shards)."""
+        """The full array on every rank (allgather; ragged blocks are padded for the exchange)."""
         if self.placement == "replicated" or _state["world"] == 1:
             return self.local
-        assert self.shape[0] % _state["world"] == 0, "allgather needs the leading extent to divide evenly"
-        return allgather(self.local)
+        return allgather_ragged(self.local, self.shape[0])
 
     def to_numpy(self):
         from . import core

@@ -237,6 +237,7 @@ int al_comm_unique_id(char out[128]);                       /* rank 0: ncclGetUn
 int al_comm_init(const char id[128], int rank, int world);  /* ncclCommInitRank on the bound device */
 int al_comm_allreduce(NDArray* a, int redop);               /* in place over a contiguous array (sum/max/min/prod) */
 int al_comm_allgather(const NDArray* shard, NDArray* full); /* concatenate equal leading-dim shards */
+int al_comm_alltoall(const NDArray* send, NDArray* recv);   /* block r of send -> rank r, block r of recv <- rank r (re-sharding) */
 /* reduce_<op>(shard, dims) completed across ranks when dims contains axis 0; the full keepdims result on every
  * rank. One node: the local reduce kernel stores into CUDA-IPC peer windows over NVLink and the partials are
  * combined in rank order (deterministic); otherwise local reduce + ncclAllReduce. Collective call. */

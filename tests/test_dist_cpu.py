@@ -109,3 +109,32 @@ def test_sharded_plans_match_the_oracle_over_gloo(world, tmp_path):
         assert np.array_equal(p["rall"], orc.reduce("sum", X, None))
     win = np.lib.stride_tricks.as_strided(base, shape=(base.size - 63, 64), strides=(4, 4))
     assert np.array_equal(cat("win"), orc.reduce("sum", win, (1,)))
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+@pytest.mark.parametrize("shape,perm", [((24, 48), (1, 0)), ((24, 6, 48), (2, 0, 1)), ((24, 6, 48), (2, 1, 0)), ((24, 48, 5), (1, 2, 0)),
+                                        ((24, 5, 48, 3), (2, 3, 0, 1)), ((24, 48), (0, 1)), ((24, 6, 48), (0, 2, 1)), ((10, 48), (1, 0)),
+                                        ((24, 7), (1, 0))])
+def test_reshard_plan_reproduces_the_global_transpose(world, shape, perm):
+    """ShardedArray.transpose's plan, with the all-to-all played out in NumPy: every rank must end up with its
+    leading-axis block of the globally transposed array."""
+    g = np.arange(int(np.prod(shape)), dtype=np.float32).reshape(shape)
+    want = np.transpose(g, perm)
+    plan = dist.reshard_plan(shape, perm, world)
+    assert plan["shape"] == want.shape
+    locals_ = [g[slice(*dist.shard_bounds(shape[0], r, world))] for r in range(world)]
+    if plan["how"] == "local":
+        assert perm[0] == 0
+        got = [np.transpose(x, perm) for x in locals_]
+    elif plan["how"] == "gather":
+        assert shape[0] % world or want.shape[0] % world
+        return
+    else:
+        pieces = [np.ascontiguousarray(np.transpose(x, perm)).reshape(world, -1) for x in locals_]  # block j -> rank j
+        got = []
+        for j in range(world):
+            recv = np.stack([pieces[i][j] for i in range(world)])  # block i <- rank i
+            got.append(np.transpose(recv.reshape(plan["recv_view"]), plan["interleave"]).reshape(plan["local_shape"]))
+    for r in range(world):
+        lo, hi = dist.shard_bounds(want.shape[0], r, world)
+        np.testing.assert_array_equal(got[r], want[lo:hi])

@@ -76,6 +76,21 @@ r = (SX - 1.0).reduce_max(dims=(1, 3))
 assert r.placement == "sharded"
 check("ShardedArray reduce_max (1,3)", r.to_numpy(), orc.reduce("max", orc.binary("sub", X, 1.0), (1, 3)))
 
+# ---- re-sharding: transpose of a sharded array (local / one all-to-all / gather fallback), ragged gather ----
+for shape, perm in [((8 * world, 16 * world), (1, 0)), ((4 * world, 6, 8 * world), (2, 0, 1)), ((4 * world, 6, 8 * world), (2, 1, 0)),
+                    ((4 * world, 8 * world, 5), (1, 2, 0)), ((4 * world, 6, 10), (0, 2, 1)), ((4 * world + 1, 8 * world), (1, 0)),
+                    ((4 * world, 8 * world + 3), (1, 0))]:
+    G = rng.standard_normal(shape).astype(np.float32)
+    T = dist.ShardedArray.scatter(G).transpose(perm)
+    how = dist.reshard_plan(shape, perm, world)["how"]
+    lo, hi = dist.shard_bounds(T.shape[0], rank, world)
+    check(f"transpose {shape} {perm} [{how}] local", al.to_numpy(T.local), np.transpose(G, perm)[lo:hi])
+    check(f"transpose {shape} {perm} [{how}] gathered", T.to_numpy(), np.transpose(G, perm))
+# config C5b with BOTH operands globally sharded: X.T + Y needs the column blocks of X (one all-to-all)
+m = 64 * world
+Xg, Yg = rng.standard_normal((m, m)).astype(np.float32), rng.standard_normal((m, m)).astype(np.float32)
+check("sharded X.T + Y", (dist.ShardedArray.scatter(Xg).transpose((1, 0)) + dist.ShardedArray.scatter(Yg)).to_numpy(), orc.binary("sum", Xg.T, Yg))
+
 # ---- the cross-GPU reduce itself: peer-memory windows (default) against the oracle, against NCCL, across ranks ----
 import ctypes as C  # noqa: E402
 import hashlib  # noqa: E402
@@ -103,6 +118,13 @@ for shape, dims, op in [((L, 7, 13), (0,), "sum"), ((L, 7, 13), (0,), "max"), ((
         got = al.to_numpy(dist.reduce_sharded(Gs, op, dims))
         check(f"peer {op} {shape} {dims} #{rep}", got, orc.reduce(op, G, dims))
         same_on_all_ranks(f"peer {op} {shape} {dims}", got)
+# in-place allreduce of an already materialised array (same windows: push, combine, collect)
+for n_el in (1, 5, 4096, 100003):
+    parts = rng.integers(-8, 9, size=(world, n_el)).astype(np.float32)
+    for op, fold in (("sum", np.sum), ("max", np.max), ("min", np.min)):
+        mine = al.from_numpy(parts[rank].copy())
+        dist.allreduce(mine, op)
+        check(f"allreduce {op} n={n_el}", al.to_numpy(mine), fold(parts, axis=0).astype(np.float32))
 # transposed shard: kept axis not unit-stride -> local reduce + push
 G = rng.integers(-8, 9, size=(L, 48, 20)).astype(np.float32)
 Gt = dist.scatter_from_numpy(G).transpose((0, 2, 1))

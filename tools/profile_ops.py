@@ -16,6 +16,9 @@ A, B, c = rnd((L, 1, 4096), 1), rnd((1, 1024, 4096), 2), rnd((4096,), 3)
 X = rnd((64 // scale, 512, 512, 64), 4)
 m = 16384 if scale == 1 else 8192
 X5, Y5 = rnd((m, m), 5), rnd((m, m), 6)
+# shapes off the BASELINE configs that exercise the fallback kernels (ew_run modes, reduce_inner_peel, reduce_window_any)
+P3, p3 = rnd(((1 << 26) // scale, 3), 7), rnd((3,), 8)
+R255 = rnd(((1 << 20) // scale, 255), 9)
 for rep in range(2):
     r = a + b; del r
     r = a * b; del r
@@ -29,5 +32,8 @@ for rep in range(2):
     r = X5.transpose((1, 0)) + Y5; del r
     r = X5.transpose((1, 0)).reshape((m * m,)); del r
     r = (al.lazy(A) + B + c).eval(); del r
+    r = P3 + p3; del r
+    r = R255.reduce_sum(dims=(1,)); del r
+    r = a.as_strided(shape=(n - 99, 100), stride=(1, 1)).reduce_sum(dims=[1]); del r
 al.synchronize()
 print("profile_ops done")
