@@ -3,6 +3,9 @@
 // from shared memory, cp.async.bulk shared->global. Kept as the measured answer to "would TMA-style
 // staging beat plain 128-bit loads on this path?" -- see DESIGN.md (it does not: both sit at the DRAM
 // ceiling, which is why the default kernels use LDG.128/STG.128).
+// Caution: thread 0 issues the bulk copies right after __syncthreads(); a later TMA experiment on the window
+// kernel found that BAR.SYNC.DEFER_BLOCKING does not hold back a following bulk-async
+// instruction. No mismatch has been observed with this kernel, but it is opt-in for that reason too.
 #pragma once
 #include "elementwise.cuh"
 
