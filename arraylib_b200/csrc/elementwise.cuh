@@ -135,7 +135,9 @@ struct NdArgs {
     unsigned char out_aligned;  // ew_run: the output pointer is 16-byte aligned (128-bit stores allowed)
     // ew_run: how each operand is addressed. 0 = congruent with the output and 16-byte aligned (one 128-bit load),
     // 1 = "block broadcast": unit-stride over one run of axes and stride 0 over all others, so that the offset
-    // of output element e is (e / blk_inner) mod blk_len, 2 = anything else (row offsets + inner stride).
+    // of output element e is (e / blk_inner) mod blk_len, 3 = broadcast "in the middle" (contiguous below and above
+    // a run of stride-0 axes, the [N,1,C] of pairwise [N,1,C] o [1,M,C]): offset = e mod blk_inner + blk_inner *
+    // (e / blk_len), 2 = anything else (row offsets + inner stride).
     unsigned char mode[NIN];
     uint32_t blk_inner[NIN], blk_len[NIN];
     FastDiv blk_inner_div[NIN], blk_len_div[NIN];
@@ -265,6 +267,8 @@ __global__ void __launch_bounds__(kEwThreads) ew_nd_kernel(const NdArgs<F::NIN> 
 //           NumPy-style broadcasting of a contiguous array produces when its non-1 extents are adjacent
 //           ((3,), (N,1), (1,C,1,1), a scalar ...): offset(e) = (e / inner) mod len, resolved with two
 //           mul-hi divisions per THREAD and stepped with two compare/selects per element;
+//   mode 3  broadcast in the middle ([N,1,C] against [1,M,C] with a small odd C): offset(e) = e mod C + C * (e / (M*C)),
+//           three divisions per thread, three compare/selects per element;
 //   mode 2  anything else: the 4 outputs lie in at most three consecutive rows (a row = one pass over
 //           the inner axis), so the offsets of rows q, q+1 (q+2 only when the inner extent is 2) are
 //           resolved once and every element is row offset + inner index * inner stride.
@@ -317,6 +321,19 @@ __global__ void __launch_bounds__(kEwThreads) ew_run_kernel(const NdArgs<F::NIN>
                     c = 0;
                     if (++o == len) o = 0;
                 }
+            }
+        } else if (a.mode[i] == 3) {
+            const uint32_t p1 = a.blk_inner[i], p2 = a.blk_len[i];
+            const uint32_t q2 = fdiv(e0, a.blk_len_div[i]);
+            uint32_t r2 = e0 - q2 * p2;
+            uint32_t r1 = r2 - fdiv(r2, a.blk_inner_div[i]) * p1;
+            long long o = (long long)q2 * p1 + r1;
+#pragma unroll
+            for (int j = 0; j < kRun; j++) {
+                if (e0 + j < a.n_items) v[j][i] = __ldg(a.in[i] + o);
+                o++, r1++, r2++;
+                if (r1 == p1) r1 = 0, o -= p1;
+                if (r2 == p2) r2 = 0, o += p1;
             }
         } else {
             general = true;
@@ -942,6 +959,23 @@ static bool launch_nd_one(const F& f, const Folded& fo, const float* const* in, 
             a.mode[i] = !block ? 2 : (congruent && (uintptr_t)in[i] % 16 == 0 ? 0 : 1);
             a.blk_inner[i] = (uint32_t)(block ? inner : 1);
             a.blk_len[i] = (uint32_t)(block ? len : 1);
+            if (!block && d1 == 0 && d2 > 0 && d2 < fo.ndim && len < (1ull << 31)) {
+                // contiguous over [0, d2), stride 0 over [d2, d3), contiguous again (as if the middle were absent) above
+                int d3 = d2;
+                uint64_t p2 = len;  // = prod extent[0..d2)
+                while (d3 < fo.ndim && fo.in_stride[i][d3] == 0) p2 *= fo.extent[d3++];
+                bool middle = d3 < fo.ndim;
+                int64_t expect = (int64_t)len;
+                for (int d = d3; d < fo.ndim && middle; d++) {
+                    middle = fo.in_stride[i][d] == expect;
+                    expect *= (int64_t)fo.extent[d];
+                }
+                if (middle && p2 < (1ull << 31)) {
+                    a.mode[i] = 3;
+                    a.blk_inner[i] = (uint32_t)len;
+                    a.blk_len[i] = (uint32_t)p2;
+                }
+            }
             a.blk_inner_div[i] = make_fastdiv(a.blk_inner[i]);
             a.blk_len_div[i] = make_fastdiv(a.blk_len[i]);
         }

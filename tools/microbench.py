@@ -223,7 +223,8 @@ def bench_ew_sweep():
     cases = [((1 << 14, 1), (1, 1 << 14)), ((1 << 14, 1 << 14), (1 << 14, 1)), ((1 << 14, 1 << 14), (1, 1 << 14)),
              ((1 << 28,), (1,)), ((1,), (1 << 28,)), ((64, 1, 512, 512), (1, 16, 1, 1)), ((64, 16, 512, 512), (1, 16, 1, 1)),
              ((64, 16, 512, 512), (64, 1, 512, 512)), ((64, 16, 512, 512), (512, 1)), ((1 << 20, 1, 16), (1, 16, 16)),
-             ((4096, 1, 4096, 1), (1, 4, 1, 4)), ((1 << 26, 3), (3,)), ((1 << 26, 3), (1 << 26, 1)), ((1 << 22, 1, 7), (1, 9, 7))]
+             ((4096, 1, 4096, 1), (1, 4, 1, 4)), ((1 << 26, 3), (3,)), ((1 << 26, 3), (1 << 26, 1)), ((1 << 22, 1, 7), (1, 9, 7)),
+             ((1 << 14, 1, 3), (1, 1 << 12, 3)), ((1 << 12, 1, 5, 3), (1, 1 << 11, 1, 3))]
     for sa, sb in cases:
         A, B = rnd(sa, 1), rnd(sb, 2)
         out_shape = np.broadcast_shapes(sa, sb)
