@@ -260,19 +260,20 @@ __global__ void __launch_bounds__(kEwThreads) ew_nd_kernel(const NdArgs<F::NIN> 
 // The fallback for everything the 128-bit plans cannot take (odd inner extents, misaligned rows,
 // arbitrary as_strided operands). Resolving a linear index costs a divmod chain per operand; with one
 // output per thread that put ~60-90 instructions on every element and capped write-bound cases at
-// 1.5-2 TB/s. Here a thread owns 4 consecutive outputs (one 128-bit store when the output is aligned)
+// 1.5-2 TB/s. Here a thread owns 8 consecutive outputs (two 128-bit stores when the output is aligned)
 // and each operand is addressed in the cheapest way its layout allows:
 //   mode 0  congruent with the output (the big stream of "(N,3) + (3,)"): one 128-bit load, no index;
 //   mode 1  block broadcast -- unit-stride over one run of axes, stride 0 over the rest, which is what
 //           NumPy-style broadcasting of a contiguous array produces when its non-1 extents are adjacent
 //           ((3,), (N,1), (1,C,1,1), a scalar ...): offset(e) = (e / inner) mod len, resolved with two
 //           mul-hi divisions per THREAD and stepped with two compare/selects per element;
+//   mode 4  mode 1 with inner = 1, a period that is a multiple of 8 and an aligned base: two 128-bit loads;
 //   mode 3  broadcast in the middle ([N,1,C] against [1,M,C] with a small odd C): offset(e) = e mod C + C * (e / (M*C)),
 //           three divisions per thread, three compare/selects per element;
 //   mode 2  anything else: the 4 outputs lie in at most three consecutive rows (a row = one pass over
 //           the inner axis), so the offsets of rows q, q+1 (q+2 only when the inner extent is 2) are
 //           resolved once and every element is row offset + inner index * inner stride.
-constexpr int kRun = 4;
+constexpr int kRun = 8;  // outputs per thread: the per-thread index set-up of modes 1-3 is paid once per 8 outputs
 
 template <int NIN>
 __device__ __forceinline__ void run_row_offsets(const NdArgs<NIN>& a, uint32_t q, long long* off) {
@@ -306,10 +307,21 @@ __global__ void __launch_bounds__(kEwThreads) ew_run_kernel(const NdArgs<F::NIN>
 #pragma unroll
     for (int i = 0; i < NIN; i++) {
         if (a.mode[i] == 0 && full) {
-            const float4 d = __ldcs(reinterpret_cast<const float4*>(a.in[i] + e0));
-            v[0][i] = d.x, v[1][i] = d.y, v[2][i] = d.z, v[3][i] = d.w;
-        } else if (a.mode[i] <= 1) {
-            // mode 0 on a ragged tail is the block formula with inner = 1, len = all (set up by the host)
+#pragma unroll
+            for (int h = 0; h < kRun / 4; h++) {
+                const float4 d = __ldcs(reinterpret_cast<const float4*>(a.in[i] + e0) + h);
+                v[4 * h][i] = d.x, v[4 * h + 1][i] = d.y, v[4 * h + 2][i] = d.z, v[4 * h + 3][i] = d.w;
+            }
+        } else if (a.mode[i] == 4 && full) {
+            // periodic, contiguous, period a multiple of kRun, aligned: the run never wraps and is two 128-bit loads
+            const uint32_t o = e0 - fdiv(e0, a.blk_len_div[i]) * a.blk_len[i];
+#pragma unroll
+            for (int h = 0; h < kRun / 4; h++) {
+                const float4 d = __ldg(reinterpret_cast<const float4*>(a.in[i] + o) + h);
+                v[4 * h][i] = d.x, v[4 * h + 1][i] = d.y, v[4 * h + 2][i] = d.z, v[4 * h + 3][i] = d.w;
+            }
+        } else if (a.mode[i] <= 1 || a.mode[i] == 4) {
+            // mode 0 / 4 on a ragged tail is the block formula with inner = 1, len = all (set up by the host)
             const uint32_t inner = a.blk_inner[i], len = a.blk_len[i];
             const uint32_t t = fdiv(e0, a.blk_inner_div[i]);
             uint32_t c = e0 - t * inner;
@@ -341,34 +353,40 @@ __global__ void __launch_bounds__(kEwThreads) ew_run_kernel(const NdArgs<F::NIN>
     }
     if (general) {
         const uint32_t ext0 = a.extent[0];
-        const uint32_t q0 = fdiv(e0, a.div[0]);
-        const uint32_t r0 = e0 - q0 * ext0;
-        long long row[3][NIN];
-        run_row_offsets<NIN>(a, q0, row[0]);
-        if (r0 + (kRun - 1) >= ext0) {  // the run crosses into the next row(s): rare when rows are long
-            run_row_offsets<NIN>(a, q0 + 1, row[1]);
-            if (ext0 == 2) {
-                run_row_offsets<NIN>(a, q0 + 2, row[2]);
-            } else {
 #pragma unroll
-                for (int i = 0; i < NIN; i++) row[2][i] = row[1][i];
-            }
-        } else {
+        for (int h = 0; h < kRun / 4; h++) {  // four outputs at a time: they lie in at most three consecutive rows
+            const uint32_t eh = e0 + 4 * h;
+            if (eh < a.n_items) {
+                const uint32_t q0 = fdiv(eh, a.div[0]);
+                const uint32_t r0 = eh - q0 * ext0;
+                long long row[3][NIN];
+                run_row_offsets<NIN>(a, q0, row[0]);
+                if (r0 + 3 >= ext0) {  // the run crosses into the next row(s): rare when rows are long
+                    run_row_offsets<NIN>(a, q0 + 1, row[1]);
+                    if (ext0 == 2) {
+                        run_row_offsets<NIN>(a, q0 + 2, row[2]);
+                    } else {
 #pragma unroll
-            for (int i = 0; i < NIN; i++) row[1][i] = row[2][i] = row[0][i];
-        }
+                        for (int i = 0; i < NIN; i++) row[2][i] = row[1][i];
+                    }
+                } else {
 #pragma unroll
-        for (int j = 0; j < kRun; j++) {
-            uint32_t r = r0 + j;
-            int c = 0;
-            if (r >= ext0) r -= ext0, c = 1;
-            if (r >= ext0) r -= ext0, c = 2;
-            if (e0 + j < a.n_items) {
+                    for (int i = 0; i < NIN; i++) row[1][i] = row[2][i] = row[0][i];
+                }
 #pragma unroll
-                for (int i = 0; i < NIN; i++) {
-                    if (a.mode[i] == 2) {
-                        const long long base = c == 0 ? row[0][i] : (c == 1 ? row[1][i] : row[2][i]);
-                        v[j][i] = __ldg(a.in[i] + base + (long long)r * a.stride[i][0]);
+                for (int j = 0; j < 4; j++) {
+                    uint32_t r = r0 + j;
+                    int c = 0;
+                    if (r >= ext0) r -= ext0, c = 1;
+                    if (r >= ext0) r -= ext0, c = 2;
+                    if (eh + j < a.n_items) {
+#pragma unroll
+                        for (int i = 0; i < NIN; i++) {
+                            if (a.mode[i] == 2) {
+                                const long long base = c == 0 ? row[0][i] : (c == 1 ? row[1][i] : row[2][i]);
+                                v[4 * h + j][i] = __ldg(a.in[i] + base + (long long)r * a.stride[i][0]);
+                            }
+                        }
                     }
                 }
             }
@@ -379,9 +397,12 @@ __global__ void __launch_bounds__(kEwThreads) ew_run_kernel(const NdArgs<F::NIN>
     for (int j = 0; j < kRun; j++) r[j] = (e0 + j < a.n_items) ? f(v[j]) : 0.0f;
     float* dst = a.out + e0;
     if (full) {
-        const float4 r4 = make_float4(r[0], r[1], r[2], r[3]);
-        if (a.stream_store) __stcs(reinterpret_cast<float4*>(dst), r4);
-        else *reinterpret_cast<float4*>(dst) = r4;
+#pragma unroll
+        for (int h = 0; h < kRun / 4; h++) {
+            const float4 r4 = make_float4(r[4 * h], r[4 * h + 1], r[4 * h + 2], r[4 * h + 3]);
+            if (a.stream_store) __stcs(reinterpret_cast<float4*>(dst) + h, r4);
+            else reinterpret_cast<float4*>(dst)[h] = r4;
+        }
     } else {
 #pragma unroll
         for (int j = 0; j < kRun; j++)
@@ -957,6 +978,7 @@ static bool launch_nd_one(const F& f, const Folded& fo, const float* const* in, 
             block = block && inner < (1ull << 31) && len < (1ull << 31);
             const bool congruent = block && d1 == 0 && d2 == fo.ndim;
             a.mode[i] = !block ? 2 : (congruent && (uintptr_t)in[i] % 16 == 0 ? 0 : 1);
+            if (a.mode[i] == 1 && inner == 1 && len % kRun == 0 && (uintptr_t)in[i] % 16 == 0) a.mode[i] = 4;  // periodic, vectorisable
             a.blk_inner[i] = (uint32_t)(block ? inner : 1);
             a.blk_len[i] = (uint32_t)(block ? len : 1);
             if (!block && d1 == 0 && d2 > 0 && d2 < fo.ndim && len < (1ull << 31)) {

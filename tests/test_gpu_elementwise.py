@@ -305,6 +305,7 @@ def test_errors_raise_instead_of_aborting(al):
 
 @pytest.mark.parametrize("sa,sb", [((50001, 3), (3,)), ((3,), (50001, 3)), ((50001, 3), (50001, 1)), ((4001, 1, 7), (1, 9, 7)),
                                    ((301, 1, 3), (1, 257, 3)), ((2, 33, 1, 1, 5), (1, 1, 7, 3, 5)), ((33, 1, 5, 3), (1, 29, 1, 3)),
+                                   ((301, 1, 3), (1, 256, 3)), ((1000, 24), (24,)), ((1000, 3, 8), (3, 8)), ((77, 1, 6), (1, 40, 6)),
                                    ((1000, 5, 3), (5, 1)), ((333, 3), (333, 3)), ((2, 50001), (2, 1))])
 @pytest.mark.parametrize("op", ["sum", "sub", "div", "max", "lt"])
 def test_odd_inner_extents_congruent_operand_takes_128_bit_loads(al, orc, rng, sa, sb, op):
