@@ -49,8 +49,39 @@ size_t count_of(const size_t* shape, size_t ndim) {
     return n;
 }
 
+// Asynchronous uploads (array_fill_async) run on the H2D stream. The compute stream does NOT wait for an upload
+// when it is enqueued -- that would hold the next kernel back until every upload queued so far has landed --
+// but when the uploaded buffer is first USED: every entry point validates its operands, and valid() makes the
+// compute stream wait for the operand's own upload event. So `upload a, b, X; a + b` starts as soon as a and b
+// are resident while X is still travelling (and the D2H of a + b overlaps it: PCIe is full duplex).
+static std::unordered_map<const Data*, cudaEvent_t> g_uploads;
+static std::vector<cudaEvent_t> g_event_pool;
+
+static cudaEvent_t take_event() {
+    if (!g_event_pool.empty()) {
+        cudaEvent_t e = g_event_pool.back();
+        g_event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    return e;
+}
+
+static void await_upload(const Data* d) {
+    if (g_uploads.empty()) return;
+    auto it = g_uploads.find(d);
+    if (it == g_uploads.end()) return;
+    cudaStreamWaitEvent(g_rt.stream, it->second, 0);
+    g_event_pool.push_back(it->second);
+    g_uploads.erase(it);
+}
+
 bool valid(const NDArray* a, const char* who) {
-    if (a && a->data && a->lay && a->lay->ndim > 0 && a->ptr) return true;
+    if (a && a->data && a->lay && a->lay->ndim > 0 && a->ptr) {
+        await_upload(a->data);
+        return true;
+    }
     set_error("TypeError: %s got a NULL or malformed array", who);
     return false;
 }
@@ -296,6 +327,8 @@ int al_sync(void) {
               cuda_ok(cudaStreamSynchronize(g_rt.stream), "cudaStreamSynchronize") &&
               cuda_ok(cudaStreamSynchronize(g_rt.d2h_stream), "cudaStreamSynchronize(d2h)");
     drain_pending_downloads();
+    for (auto& kv : g_uploads) g_event_pool.push_back(kv.second);  // the H2D stream is idle: nothing left to wait for
+    g_uploads.clear();
     if (ok && comm_error_pending()) ok = false;  // a peer-memory collective gave up waiting for another rank
     return ok ? 0 : -1;
 }
@@ -488,6 +521,7 @@ void array_free(NDArray* a) {
         return;
     }
     if (a->data && __atomic_sub_fetch(&a->data->refs, 1, __ATOMIC_ACQ_REL) == 0) {
+        await_upload(a->data);  // never used: the block must still not be recycled before its upload has landed
         g_rt.bytes_in_use -= a->data->size * sizeof(float);
         device_free(a->data->mem);
         free(a->data);
@@ -535,9 +569,9 @@ NDArray* array_fill(f32* elems, const size_t* shape, size_t ndim) {
     return a;
 }
 
-// Asynchronous upload (extension): the copy runs on a dedicated H2D stream and the compute stream
-// waits for it, so the call returns at once and overlaps with downloads and kernels. `elems` must
-// be pinned (al_host_alloc) and stay untouched until al_sync().
+// Asynchronous upload (extension): the copy runs on a dedicated H2D stream; the compute stream waits for it
+// when the array is first used, so the call returns at once and overlaps with downloads, kernels and the
+// uploads of other arrays. `elems` must be pinned (al_host_alloc) and stay untouched until al_sync().
 NDArray* array_fill_async(f32* elems, const size_t* shape, size_t ndim) {
     AL_ENTER;
     AL_REQUIRE(elems, "TypeError: array_fill_async got a NULL host buffer");
@@ -547,9 +581,13 @@ NDArray* array_fill_async(f32* elems, const size_t* shape, size_t ndim) {
     bool ok = cuda_ok(cudaEventRecord(g_rt.ev_copy, g_rt.stream), "cudaEventRecord") &&
               cuda_ok(cudaStreamWaitEvent(g_rt.h2d_stream, g_rt.ev_copy, 0), "cudaStreamWaitEvent") &&
               cuda_ok(cudaMemcpyAsync(a->ptr, elems, a->data->size * sizeof(float), cudaMemcpyHostToDevice,
-                                      g_rt.h2d_stream), "cudaMemcpyAsync(H2D)") &&
-              cuda_ok(cudaEventRecord(g_rt.ev_copy, g_rt.h2d_stream), "cudaEventRecord") &&
-              cuda_ok(cudaStreamWaitEvent(g_rt.stream, g_rt.ev_copy, 0), "cudaStreamWaitEvent");
+                                      g_rt.h2d_stream), "cudaMemcpyAsync(H2D)");
+    if (ok) {  // the compute stream waits for this event when the array is first used (valid())
+        cudaEvent_t landed = take_event();
+        ok = landed && cuda_ok(cudaEventRecord(landed, g_rt.h2d_stream), "cudaEventRecord");
+        if (ok) g_uploads[a->data] = landed;
+        else if (landed) g_event_pool.push_back(landed);
+    }
     if (!ok) {
         std::string keep = g_err;
         array_free(a);

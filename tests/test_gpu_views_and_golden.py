@@ -187,6 +187,32 @@ def test_async_host_transfers(al, rng):
     assert_bit_equal(hout.reshape(70, 3, 1000), np.transpose(hin, (2, 0, 1)), "async transposed")
 
 
+def test_uploads_are_awaited_per_array_at_first_use(al, rng):
+    """An async upload does not stall the compute stream; the first op that touches the array waits for that
+    array's own upload. Big upload first, small ones after it, ops on the small ones, then on the big one;
+    uploads that are never used (freed at once) must not let the recycled block be overwritten early."""
+    big = al.host_buffer((1 << 26,))  # 256 MiB: still on the bus while the small operands are used
+    big[:] = rng.standard_normal(big.shape).astype(np.float32)
+    sa, sb = al.host_buffer((100003,)), al.host_buffer((100003,))
+    sa[:], sb[:] = rng.standard_normal(sa.shape).astype(np.float32), rng.standard_normal(sb.shape).astype(np.float32)
+    for rep in range(3):
+        X = al.from_numpy(big, blocking=False)
+        A, B = al.from_numpy(sa, blocking=False), al.from_numpy(sb, blocking=False)
+        small = A * B + 1.0
+        first = al.to_numpy(small)                       # blocking download while X may still be in flight
+        assert_bit_equal(first, sa * sb + np.float32(1.0), "small operands")
+        view = X[1:1 + (1 << 20)]                        # a view shares the upload of its base
+        assert_bit_equal(al.to_numpy(view + 2.0), big[1:1 + (1 << 20)] + np.float32(2.0), "view of a pending upload")
+        assert float(X[12345]) == float(big[12345])
+        unused = al.from_numpy(big, blocking=False)      # never used: freed while its upload is pending ...
+        del unused
+        Z = al.zeros((1 << 26,)) + 3.0                   # ... its block is recycled here and must end up all 3.0
+        assert_bit_equal(al.to_numpy(al.reduce_max(Z)), np.float32([3.0]), "recycled block")
+        assert_bit_equal(al.to_numpy(al.reduce_min(Z)), np.float32([3.0]), "recycled block")
+        del X, A, B, Z
+    al.synchronize()
+
+
 def test_device_out_of_memory_raises_and_recovers(al):
     """A request beyond the 180 GB of HBM raises MemoryError (the reference would abort the process);
     the cache is handed back to the driver on the way and the library keeps working."""
