@@ -114,7 +114,7 @@ NDArray* array_full(const size_t* shape, size_t ndim, f32 value);   /* extension
 
 /* ---- host materialisation (replaces core.py:189,193,340-363 which read Data.mem directly) - */
 int array_to_host(const NDArray* src, f32* dst);                    /* logical view -> contiguous host buffer of prod(shape) */
-NDArray* array_fill_async(f32* elems, const size_t* shape, size_t ndim); /* extension: upload from PINNED memory on the H2D stream; returns at once */
+NDArray* array_fill_async(f32* elems, const size_t* shape, size_t ndim); /* extension: upload from PINNED memory on the H2D stream; returns at once; the compute stream waits for it when the array is first used */
 int array_to_host_async(const NDArray* src, f32* dst);              /* extension: download to PINNED memory on the D2H stream; dst valid after al_sync() */
 int array_read_base(const NDArray* src, size_t offset, size_t count, f32* dst); /* raw base buffer elements */
 int array_write_base(NDArray* dst, size_t offset, size_t count, const f32* src);
