@@ -120,3 +120,16 @@ def test_random_float_sums_within_tolerance(al, orc, seed):
         n = int(np.prod([a.shape[d] for d in dims])) if dims else 1
         tol = 2.0 * n * 2.0 ** -24 * np.sum(np.abs(a.astype(np.float64)), axis=dims, keepdims=True) if dims else np.zeros_like(want)
         assert np.all(np.abs(got - want) <= tol + 0.0), f"seed {seed} {a.shape} {dims}"
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_short_fuzz_campaign_with_large_lopsided_shapes(seed):
+    """tools/fuzz.py for a few seconds: the same differential idea with shapes up to 2M elements (tiny odd inner
+    extents under long outer axes, operands broadcast in the middle, misaligned bases, window widths 8..1024)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz.py"), "8", str(seed)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "fuzz ok" in res.stdout
