@@ -30,21 +30,24 @@ struct ChainArgs {
 };
 
 // One chain step over N lanes. The op is decoded ONCE (the switch is outside the lane loops), so the
-// interpreter costs a handful of instructions per step per thread, not per element.
+// interpreter costs a handful of instructions per step per thread, not per element. The steps use the
+// *_raw functions: a fused chain is issue-bound, and the per-element NaN fix-up of the eager kernels
+// (x86 sign and payload, elementwise.cuh) cost 2.5 -> 6.0 ms on the C3 chain. Every non-NaN result is
+// bit-identical to the eager path; a NaN result is the GPU's canonical NaN.
 template <int OP, int N>
 __device__ __forceinline__ void lanes_bin(float* acc, const float* other, bool reversed) {
     if (reversed) {
 #pragma unroll
-        for (int c = 0; c < N; c++) acc[c] = binop_apply<OP>(other[c], acc[c]);
+        for (int c = 0; c < N; c++) acc[c] = binop_raw<OP>(other[c], acc[c]);
     } else {
 #pragma unroll
-        for (int c = 0; c < N; c++) acc[c] = binop_apply<OP>(acc[c], other[c]);
+        for (int c = 0; c < N; c++) acc[c] = binop_raw<OP>(acc[c], other[c]);
     }
 }
 template <int OP, int N>
 __device__ __forceinline__ void lanes_un(float* acc) {
 #pragma unroll
-    for (int c = 0; c < N; c++) acc[c] = ufunc_apply<OP>(acc[c]);
+    for (int c = 0; c < N; c++) acc[c] = ufunc_raw<OP>(acc[c]);
 }
 
 template <bool FULL, int N>

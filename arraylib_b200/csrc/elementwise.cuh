@@ -27,17 +27,52 @@ namespace al {
 
 
 // ---- scalar functions: bit-for-bit the reference's (arraylib.c:12-49) ---------------------------
+// NaN results follow the reference's x86-64 build as well (probed through the compiled oracle; only the
+// rare NaN lane takes these paths): an SSE arithmetic op returns its FIRST NaN operand, quieted, and the
+// negative default NaN 0xFFC00000 when it creates one (inf - inf, 0 * inf, 0 / 0); glibc's double
+// functions hand a NaN argument back (quieted by the float -> double conversion) and create a negative
+// NaN on a domain error, except asin / acos, whose NaN is positive. The GPU would return the canonical
+// 0x7FFFFFFF everywhere.
+// Sign-bit edits as opaque integer instructions: written in C++ the optimiser turns `bits ^ 0x80000000` into
+// neg.f32 and `bits & 0x7fffffff` into abs.f32, and those return the canonical NaN for a NaN input.
+__device__ __forceinline__ float flip_sign_bit(float x) {
+    uint32_t b;
+    asm("xor.b32 %0, %1, 0x80000000;" : "=r"(b) : "r"(__float_as_uint(x)));
+    return __uint_as_float(b);
+}
+__device__ __forceinline__ float clear_sign_bit(float x) {
+    uint32_t b;
+    asm("and.b32 %0, %1, 0x7fffffff;" : "=r"(b) : "r"(__float_as_uint(x)));
+    return __uint_as_float(b);
+}
+__device__ __forceinline__ float nan_quiet(float x) {
+    uint32_t b;
+    asm("or.b32 %0, %1, 0x00400000;" : "=r"(b) : "r"(__float_as_uint(x)));
+    return __uint_as_float(b);
+}
+__device__ __forceinline__ float nan_default_neg() { return __uint_as_float(0xFFC00000u); }
+__device__ __forceinline__ float nan_default_pos() { return __uint_as_float(0x7FC00000u); }
+__device__ __forceinline__ float nan_like_sse(float res, float l, float r) {
+    if (res == res) return res;
+    if (l != l) return nan_quiet(l);
+    if (r != r) return nan_quiet(r);
+    return nan_default_neg();
+}
+
+// *_raw: the arithmetic alone (a NaN result is whatever the GPU makes of it: the canonical 0x7FFFFFFF);
+// *_apply: the same value, and when it is a NaN, the NaN the reference's build would have produced.
 template <int OP>
-__device__ __forceinline__ float binop_apply(float l, float r) {
+__device__ __forceinline__ float binop_raw(float l, float r) {
     if constexpr (OP == AL_SUM) return __fadd_rn(l, r);
     else if constexpr (OP == AL_SUB) return __fsub_rn(l, r);
     else if constexpr (OP == AL_MUL) return __fmul_rn(l, r);
     else if constexpr (OP == AL_DIV) return __fdiv_rn(l, r);
     else if constexpr (OP == AL_MOD) return fmodf(l, r);  // fmod is exact, so f32 == round(f64)
     else if constexpr (OP == AL_POW) return (float)pow((double)l, (double)r);
-    // glibc fmax/fmin: NaN-ignoring, and on a +-0 tie the LEFT operand is returned
-    else if constexpr (OP == AL_MAX) return (l >= r || r != r) ? l : r;
-    else if constexpr (OP == AL_MIN) return (l <= r || r != r) ? l : r;
+    // gcc's inline fmax / fmin: a NaN on the left yields the right operand (whatever it is), a NaN on the right
+    // yields the left one, and on a +-0 tie the LEFT operand is returned
+    else if constexpr (OP == AL_MAX) return (l >= r || (r != r && l == l)) ? l : r;
+    else if constexpr (OP == AL_MIN) return (l <= r || (r != r && l == l)) ? l : r;
     else if constexpr (OP == AL_EQ) return l == r ? 1.0f : 0.0f;
     else if constexpr (OP == AL_NE) return l != r ? 1.0f : 0.0f;
     else if constexpr (OP == AL_GT) return l > r ? 1.0f : 0.0f;
@@ -46,13 +81,41 @@ __device__ __forceinline__ float binop_apply(float l, float r) {
     else return l <= r ? 1.0f : 0.0f;
 }
 
+template <int OP>
+__device__ __forceinline__ float binop_apply(float l, float r) {
+    const float res = binop_raw<OP>(l, r);
+    if (res == res) return res;
+    if constexpr (OP == AL_MOD) {
+        if (l != l && r != r) {  // x87 fprem rule: the NaN with the larger (quieted) significand; on a tie the positive one
+            const uint32_t fl = (__float_as_uint(l) & 0x007fffffu) | 0x00400000u, fr = (__float_as_uint(r) & 0x007fffffu) | 0x00400000u;
+            const bool take_r = fr > fl || (fr == fl && (__float_as_uint(l) >> 31));
+            return nan_quiet(take_r ? r : l);
+        }
+        return nan_like_sse(res, l, r);
+    } else if constexpr (OP == AL_POW) {
+        // glibc pow: a NaN base comes back as x*x (sign kept) and is NEGATED when the base is "negative" and the
+        // exponent an odd integer; a NaN exponent comes back as x + y; a domain error creates the negative NaN
+        if (l != l) {
+            const float q = nan_quiet(l);
+            const float ar = fabsf(r);
+            const bool odd = r == r && ar < 16777216.0f && ar == truncf(ar) && (((int)ar) & 1);
+            return ((__float_as_uint(l) >> 31) && odd) ? flip_sign_bit(q) : q;
+        }
+        return r != r ? nan_quiet(r) : nan_default_neg();
+    } else if constexpr (OP == AL_MAX || OP == AL_MIN) {
+        return nan_quiet(res);  // the operand has been through fmax's float -> double conversion, which quiets it
+    } else {
+        return nan_like_sse(res, l, r);
+    }
+}
+
 // The reference promotes to double, calls libm and rounds back (arraylib.c:31-49). sqrt/ceil/
 // floor/abs/neg are exact under that double rounding, so they stay in f32; the transcendentals
 // run in FP64 on the device and round once.
 template <int OP>
-__device__ __forceinline__ float ufunc_apply(float v) {
-    if constexpr (OP == AL_NEG) return __uint_as_float(__float_as_uint(v) ^ 0x80000000u);
-    else if constexpr (OP == AL_ABS) return __uint_as_float(__float_as_uint(v) & 0x7fffffffu);
+__device__ __forceinline__ float ufunc_raw(float v) {
+    if constexpr (OP == AL_NEG) return flip_sign_bit(v);  // bitwise in the reference too (a NaN keeps its payload, unquieted)
+    else if constexpr (OP == AL_ABS) return clear_sign_bit(v);
     else if constexpr (OP == AL_SQRT) return __fsqrt_rn(v);
     else if constexpr (OP == AL_CEIL) return ceilf(v);
     else if constexpr (OP == AL_FLOOR) return floorf(v);
@@ -74,6 +137,15 @@ __device__ __forceinline__ float ufunc_apply(float v) {
         else x = atanh(x);
         return (float)x;
     }
+}
+
+template <int OP>
+__device__ __forceinline__ float ufunc_apply(float v) {
+    const float res = ufunc_raw<OP>(v);
+    if constexpr (OP == AL_NEG) return res;
+    if (res == res) return res;
+    if (v != v) return nan_quiet(OP == AL_ABS ? res : v);  // fabs((double)x): the conversion quiets a signalling NaN
+    return (OP == AL_ASIN || OP == AL_ACOS) ? nan_default_pos() : nan_default_neg();
 }
 
 // Functors: NIN inputs in, one float out.

@@ -325,3 +325,59 @@ def test_odd_inner_extents_congruent_operand_takes_128_bit_loads(al, orc, rng, s
     B = al.from_numpy(pb)[1:b.size + 1].as_strided(shape=sb, stride=row_major(sb))
     got = getattr(al, "add" if op == "sum" else op)(A, B)
     assert_bit_equal(al.to_numpy(got), orc.binary(op, a, b), f"{op} {sa} {sb} shifted")
+
+
+def _special_values():
+    bits = [0x7FC00000, 0xFFC00000, 0x7FC12345, 0xFFD54321, 0x7F812345, 0xFF800001,  # +-qNaN, payloads, signalling NaNs
+            0x7F800000, 0xFF800000, 0x00000000, 0x80000000, 0x3F800000, 0xBF800000, 0x40000000, 0xC1000000,
+            0x3F000000, 0x40600000, 0x00012345, 0x7F61B1E6, 0xC0490FDB]
+    return np.array(bits, dtype=np.uint32).view(np.float32)
+
+
+def _assert_nan_strict(got, want, what, ulp=0):
+    """Bit-exact INCLUDING the sign and payload of NaNs; finite results within `ulp` units in the last place."""
+    got, want = np.ascontiguousarray(got, np.float32), np.ascontiguousarray(want, np.float32)
+    gb, wb = got.view(np.uint32), want.view(np.uint32)
+    nan = np.isnan(want) | np.isnan(got)
+    bad = nan & (gb != wb)
+    assert not bad.any(), f"{what}: NaN bits differ at {np.argwhere(bad)[:4].tolist()}: got {[hex(v) for v in gb[bad][:4]]} want {[hex(v) for v in wb[bad][:4]]}"
+    fin = ~nan
+    if ulp == 0:
+        assert np.array_equal(gb[fin], wb[fin]), f"{what}: finite results differ"
+    else:
+        same_sign = (gb[fin] >> 31) == (wb[fin] >> 31)
+        dist = np.abs(gb[fin].astype(np.int64) - wb[fin].astype(np.int64))
+        assert np.all((dist <= ulp) & (same_sign | (dist == 0)) | (got[fin] == want[fin])), f"{what}: more than {ulp} ulp"
+
+
+@pytest.mark.parametrize("op", ["sum", "sub", "mul", "div", "mod", "max", "min", "pow", "eq", "lt", "ge"])
+def test_nan_sign_and_payload_follow_the_reference_binary(al, orc, op):
+    """The reference is an x86-64 / glibc build: SSE ops return their first NaN operand (quieted) and create the
+    NEGATIVE default NaN, fmod follows fprem, gcc's inline fmax/fmin return the right operand when the left one is
+    NaN. The full grid of special values against the oracle, bits and all."""
+    s = _special_values()
+    l, r = np.repeat(s, s.size).reshape(s.size, s.size), np.tile(s, s.size).reshape(s.size, s.size)
+    fn = getattr(al, "add" if op == "sum" else op)
+    with np.errstate(all="ignore"):
+        want = orc.binary(op, l, r)
+    _assert_nan_strict(al.to_numpy(fn(al.from_numpy(l), al.from_numpy(r))), want, op, ulp=1 if op == "pow" else 0)
+    for scalar in (0.0, 1.0, -2.5, float("inf"), float("nan")):
+        with np.errstate(all="ignore"):
+            want = orc.binary(op, s, scalar)
+        _assert_nan_strict(al.to_numpy(fn(al.from_numpy(s), scalar)), want, f"{op} scalar {scalar}", ulp=1 if op == "pow" else 0)
+    # fused chains run the bare arithmetic (they are issue-bound): same values, NaNs wherever the eager path has NaNs,
+    # but the GPU's canonical NaN instead of the x86 sign / payload
+    if op in ("sum", "sub", "mul", "div"):
+        lazy = {"sum": lambda a, b: a + b, "sub": lambda a, b: a - b, "mul": lambda a, b: a * b, "div": lambda a, b: a / b}[op]
+        got = lazy(al.lazy(al.from_numpy(l)), al.from_numpy(r)).eval()
+        with np.errstate(all="ignore"):
+            assert_bit_equal(al.to_numpy(got), orc.binary(op, l, r), f"{op} fused")
+
+
+def test_nan_sign_and_payload_follow_the_reference_unary(al, orc):
+    s = np.concatenate([_special_values(), np.float32([2.0, -2.0, 0.25, -0.25, 1e30, -1e30, 100.0, -100.0])])
+    for op in orc.UNARY:
+        with np.errstate(all="ignore"):
+            want = orc.unary(op, s)
+        exact = op in ("neg", "abs", "sqrt", "ceil", "floor")
+        _assert_nan_strict(al.to_numpy(getattr(al, op)(al.from_numpy(s))), want, op, ulp=0 if exact else 1)
