@@ -26,8 +26,7 @@ def bits_equal(got, want):
     want = np.ascontiguousarray(want, dtype=np.float32)
     if got.shape != want.shape:
         return False
-    same = got.view(np.uint32) == want.view(np.uint32)
-    return bool(np.all(same | (np.isnan(got) & np.isnan(want))))  # x/0 and fmod(x,0): NaN sign/payload is the FPU's
+    return bool(np.array_equal(got.view(np.uint32), want.view(np.uint32)))  # strict: NaN sign and payload included
 
 
 def fail(kind, detail):
