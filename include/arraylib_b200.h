@@ -15,6 +15,9 @@
  *   - Host callbacks cannot run on the device: array_op / array_reduce (which take C function
  *     pointers in the reference) fail with NotImplementedError. Their replacements are
  *     array_op_named / array_reduce_named, which take an entry of the ufunc tables below.
+ *   - Numerics: elementwise results are bit-identical to the reference's x86-64 / glibc build, NaN sign and
+ *     payload included; reduce_sum sums in a tree (stated tolerance), and the fused
+ *     chain / tape extensions return the GPU's canonical NaN where the eager path returns the x86 one.
  *
  * Reference citations are relative to /root/reference.
  */
