@@ -121,6 +121,9 @@ def _load():
     sig("al_comm_allgather", C.c_int, ArrayP, ArrayP)
     sig("al_comm_alltoall", C.c_int, ArrayP, ArrayP)
     sig("al_comm_reduce", ArrayP, C.c_int, ArrayP, SizeP, C.c_size_t)
+    sig("al_comm_reduce_scatter", ArrayP, C.c_int, ArrayP, SizeP, C.c_size_t)
+    sig("al_comm_reduce_ex", ArrayP, C.c_int, ArrayP, SizeP, C.c_size_t, C.c_size_t, C.c_int)
+    sig("al_comm_can_scatter", C.c_int, SizeP, C.c_size_t, SizeP, C.c_size_t)
     sig("al_comm_transport", C.c_char_p)
     sig("al_comm_destroy", C.c_int)
     return lib

@@ -19,6 +19,7 @@ struct Nccl {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -50,6 +51,7 @@ static bool load_nccl() {
     AL_SYM(CommDestroy, "ncclCommDestroy")
     AL_SYM(AllReduce, "ncclAllReduce")
     AL_SYM(AllGather, "ncclAllGather")
+    AL_SYM(ReduceScatter, "ncclReduceScatter")
     AL_SYM(Send, "ncclSend")
     AL_SYM(Recv, "ncclRecv")
     AL_SYM(GroupStart, "ncclGroupStart")
@@ -76,6 +78,7 @@ struct PeerWindows {
     size_t cap_elems = 0;                       // capacity of `slots` and of `result`, in floats
     char* base[kMaxPeers] = {nullptr};          // base[rank] = own allocation, others = IPC mappings
     uint32_t epoch = 0;
+    int parity = 0;                             // slot buffer of the collective in flight (epoch parity)
     int* host_error = nullptr;                  // mapped pinned int the kernels raise on a timeout
     int* dev_error = nullptr;
     uint32_t seg = 0;                           // segment size of the operation in flight
@@ -83,8 +86,12 @@ struct PeerWindows {
 static PeerWindows g_peer;
 
 static uint32_t* win_flags(int r) { return reinterpret_cast<uint32_t*>(g_peer.base[r]); }
-static float* win_slots(int r) { return reinterpret_cast<float*>(g_peer.base[r] + kFlagBytes); }
-static float* win_result(int r) { return reinterpret_cast<float*>(g_peer.base[r] + kFlagBytes) + g_peer.cap_elems; }
+// Two slot buffers, used alternately: a rank that has finished collective e may already push its partials of
+// collective e+1 while a slower rank still combines the slots of e (the scatter variant has no second
+// hand-over that would hold it back). Buffer e%2 is reused by e+2, and nobody can be in e+2 before every rank
+// has announced e+1, i.e. has finished combining e.
+static float* win_slots(int r, int parity) { return reinterpret_cast<float*>(g_peer.base[r] + kFlagBytes) + (size_t)parity * g_peer.cap_elems; }
+static float* win_result(int r) { return reinterpret_cast<float*>(g_peer.base[r] + kFlagBytes) + 2 * g_peer.cap_elems; }
 
 static void close_windows() {
     for (int r = 0; r < g_nccl.world && r < kMaxPeers; r++) {
@@ -126,7 +133,7 @@ static bool open_windows(size_t elems) {
     }
     close_windows();
     cudaGetLastError();
-    const size_t bytes = kFlagBytes + 2 * elems * sizeof(float);
+    const size_t bytes = kFlagBytes + 3 * elems * sizeof(float);
     bool mine = true;
     char* own = nullptr;
     cudaIpcMemHandle_t handle;
@@ -229,9 +236,14 @@ __device__ __forceinline__ void hand_over(const HandOver& h) {
 }
 
 // step 1 for a partial that already sits in local memory: scatter it into the owners' slots
-__global__ void __launch_bounds__(256) peer_push_kernel(const float* __restrict__ partial, uint32_t nout, const PeerMap map) {
+__global__ void __launch_bounds__(256) peer_push_kernel(const float* __restrict__ partial, uint32_t nout, const PeerMap map, uint32_t rot) {
+    // `rot` (a multiple of 4) rotates the walk so that rank r starts with the segment of owner r: at any moment
+    // the ranks write to DIFFERENT owners instead of all converging on one GPU's NVLink ingress
     const uint32_t stride = gridDim.x * blockDim.x * 4;
-    for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) * 4; e < nout; e += stride) {
+    const uint32_t padded = (nout + 3) & ~3u;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * 4; i < padded; i += stride) {
+        uint32_t e = i + rot;
+        if (e >= padded) e -= padded;
         float* d = peer_dst(map, e);
         if (e + 4 <= nout) {
             float4 v = make_float4(partial[e], partial[e + 1], partial[e + 2], partial[e + 3]);
@@ -256,6 +268,7 @@ struct CombineArgs {
     float* result[kMaxPeers];       // &result_of_rank_r[my_rank * seg]
     uint32_t seg, count;            // count = elements of the own segment that exist (<= seg)
     float init;
+    int nres;                       // destinations: world (allreduce: every rank's result window) or 1 (scatter: local output)
 };
 // step 2: own segment = init (+) (init (+) (p0 (+) p1 (+) ... in rank order)), stored into every rank's result
 template <int OP>
@@ -276,7 +289,13 @@ __global__ void __launch_bounds__(256) peer_combine_kernel(const CombineArgs a) 
         v.y = comb<OP>(a.init, comb<OP>(a.init, v.y));
         v.z = comb<OP>(a.init, comb<OP>(a.init, v.z));
         v.w = comb<OP>(a.init, comb<OP>(a.init, v.w));
-        for (int r = 0; r < world; r++) *reinterpret_cast<float4*>(a.result[r] + e) = v;
+        if (e + 4 <= a.count) {
+            for (int r = 0; r < a.nres; r++) *reinterpret_cast<float4*>(a.result[r] + e) = v;
+        } else {  // ragged end of the last segment (only the scatter variant writes into an exactly sized array)
+            const float t[4] = {v.x, v.y, v.z, v.w};
+            for (int r = 0; r < a.nres; r++)
+                for (uint32_t k = 0; e + k < a.count; k++) a.result[r][e + k] = t[k];
+        }
     }
 }
 
@@ -332,30 +351,39 @@ bool peer_begin(uint64_t nout, PeerMap* map) {
     if (peer_error_raised()) return false;
     g_peer.seg = (uint32_t)seg;
     memset(map, 0, sizeof *map);
-    for (int o = 0; o < world; o++) map->slot[o] = win_slots(o) + (size_t)g_nccl.rank * seg;
+    g_peer.parity = (int)((g_peer.epoch + 1) & 1);
+    for (int o = 0; o < world; o++) map->slot[o] = win_slots(o, g_peer.parity) + (size_t)g_nccl.rank * seg;
     map->seg = (uint32_t)seg;
     map->segdiv = make_fastdiv((uint32_t)seg);
     map->world = world;
+    map->rank = g_nccl.rank;
     return true;
 }
 
 bool peer_push(const float* partial, uint64_t nout, const PeerMap& map) {
     unsigned blocks = (unsigned)((nout / 4 + 255) / 256 + 1);
     if (blocks > (unsigned)kNumSMs * 8) blocks = kNumSMs * 8;
-    peer_push_kernel<<<blocks, 256, 0, rt().stream>>>(partial, (uint32_t)nout, map);
+    const uint32_t rot = (uint32_t)(((uint64_t)g_nccl.rank * map.seg) % ((nout + 3) & ~3ull));
+    peer_push_kernel<<<blocks, 256, 0, rt().stream>>>(partial, (uint32_t)nout, map, rot);
     note_launch("peer_push");
     return check_launch("peer_push");
 }
 
-bool peer_finish(int redop, float* out, uint64_t nout, float init) {
+bool peer_finish(int redop, float* out, uint64_t nout, float init, bool scatter) {
     const int world = g_nccl.world, rank = g_nccl.rank;
     const uint32_t seg = g_peer.seg;
     g_peer.epoch++;
     CombineArgs c;
     memset(&c, 0, sizeof c);
     c.h = make_hand_over(0);
-    c.slots = win_slots(rank);
-    for (int r = 0; r < world; r++) c.result[r] = win_result(r) + (size_t)rank * seg;
+    c.slots = win_slots(rank, g_peer.parity);
+    if (scatter) {  // the own segment is the whole local result: one hand-over, no broadcast, no collect
+        c.nres = 1;
+        c.result[0] = out;
+    } else {
+        c.nres = world;
+        for (int r = 0; r < world; r++) c.result[r] = win_result(r) + (size_t)rank * seg;
+    }
     c.seg = seg;
     const uint64_t lo = (uint64_t)rank * seg;
     c.count = lo >= nout ? 0u : (uint32_t)(nout - lo < seg ? nout - lo : seg);
@@ -371,6 +399,7 @@ bool peer_finish(int redop, float* out, uint64_t nout, float init) {
     }
     note_launch("peer_combine");
     if (!check_launch("peer_combine")) return false;
+    if (scatter) return true;
     blocks = (unsigned)((nout / 4 + 255) / 256 + 1);
     if (blocks > (unsigned)kNumSMs * 8) blocks = kNumSMs * 8;
     peer_collect_kernel<<<blocks, 256, 0, st>>>(make_hand_over(1), win_result(rank), out, (uint32_t)nout);
@@ -418,7 +447,7 @@ int al_comm_allreduce(NDArray* a, int redop) {
     PeerMap map;
     if (peer_begin(n, &map)) {  // same windows as al_comm_reduce: push, rank-ordered combine, collect (in place)
         const float ident[AL_REDOP_COUNT] = {0.0f, -INFINITY, INFINITY, 1.0f};
-        return peer_push(a->ptr, n, map) && peer_finish(redop, a->ptr, n, ident[redop]) ? 0 : -1;
+        return peer_push(a->ptr, n, map) && peer_finish(redop, a->ptr, n, ident[redop], false) ? 0 : -1;
     }
     clear_error();
     if (!nccl_ok(g_nccl.AllReduce(a->ptr, a->ptr, n, ncclFloat32, ops[redop], g_nccl.comm, rt().stream), "ncclAllReduce"))
@@ -461,27 +490,53 @@ int al_comm_alltoall(const NDArray* send, NDArray* recv) {
     return 0;
 }
 
-NDArray* al_comm_reduce(int redop, const NDArray* shard, const size_t* dims, size_t ndims) {
-    AL_ENTER;
+// Where the flat output of a cross-GPU reduction is cut when it stays SHARDED: along its first axis with an
+// extent > 1 (the leading non-reduced axis), in `world` equal blocks that are also the flat peer segments.
+static bool scatter_axis(const size_t* dshape, size_t nd, int world, size_t* axis) {
+    for (size_t i = 0; i < nd; i++) {
+        if (dshape[i] == 1) continue;
+        const uint64_t nout = count_of(dshape, nd);
+        if (dshape[i] % (size_t)world != 0 || (nout / world) % 4 != 0) return false;
+        *axis = i;
+        return true;
+    }
+    return false;  // a full reduce has a single output: nothing to shard
+}
+
+static NDArray* comm_reduce(int redop, const NDArray* shard, const size_t* dims, size_t ndims, size_t shard_ax, bool scatter) {
     if (!valid(shard, "al_comm_reduce")) return nullptr;
     AL_REQUIRE(redop >= 0 && redop < AL_REDOP_COUNT, "ValueError: unknown reduce op %d", redop);
     const size_t nd = shard->lay->ndim;
     AL_REQUIRE(nd >= 1 && nd <= 64, "ValueError: al_comm_reduce needs 1..64 dimensions");
+    AL_REQUIRE(shard_ax < nd, "ValueError: shard axis out of bounds");
+    for (size_t i = 0; i < shard_ax; i++)
+        AL_REQUIRE(shard->lay->shape[i] == 1, "ValueError: the shard axis must be the leading non-unit axis");
     bool crosses = false;
     size_t dshape[64];
     for (size_t i = 0; i < nd; i++) dshape[i] = shard->lay->shape[i];
     for (size_t i = 0; i < ndims; i++) {
         AL_REQUIRE(dims[i] < nd, "ValueError: out of bounds");
         dshape[dims[i]] = 1;
-        crosses |= dims[i] == 0;
+        crosses |= dims[i] == shard_ax;
     }
-    if (!crosses || !g_nccl.comm || g_nccl.world == 1) return reduce_impl(redop, shard, dims, ndims, 0.0f, false);
+    if (!crosses || !g_nccl.comm || g_nccl.world == 1) {
+        AL_REQUIRE(!scatter, "ValueError: al_comm_reduce_scatter needs a communicator and a reduction over axis 0");
+        return reduce_impl(redop, shard, dims, ndims, 0.0f, false);
+    }
     if (peer_error_raised()) return nullptr;
     const float ident[AL_REDOP_COUNT] = {0.0f, -INFINITY, INFINITY, 1.0f};
     const uint64_t nout = count_of(dshape, nd);
+    size_t lshape[64], ax = 0;
+    for (size_t i = 0; i < nd; i++) lshape[i] = dshape[i];
+    if (scatter) {
+        AL_REQUIRE(scatter_axis(dshape, nd, g_nccl.world, &ax),
+                   "ValueError: the reduced shape cannot be cut into %d equal 16-byte aligned blocks along its leading axis", g_nccl.world);
+        lshape[ax] = dshape[ax] / (size_t)g_nccl.world;
+    }
     PeerMap map;
     if (peer_begin(nout, &map)) {
-        // local kernel -> owners' slots over NVLink -> rank-ordered combine -> result on every rank
+        // local kernel -> owners' slots over NVLink -> rank-ordered combine -> result on every rank (or, scatter: the
+        // own segment only)
         bool fused = false;
         if (!reduce_into_peers(redop, shard, dims, ndims, map, &fused)) return nullptr;
         if (!fused) {
@@ -493,9 +548,9 @@ NDArray* al_comm_reduce(int redop, const NDArray* shard, const size_t* dims, siz
             restore_error(keep);
             if (!ok) return nullptr;
         }
-        NDArray* out = new_array(dshape, nd);
+        NDArray* out = new_array(scatter ? lshape : dshape, nd);
         if (!out) return nullptr;
-        if (!peer_finish(redop, out->ptr, nout, ident[redop])) {
+        if (!peer_finish(redop, out->ptr, nout, ident[redop], scatter)) {
             std::string keep = last_error_string();
             array_free(out);
             restore_error(keep);
@@ -507,6 +562,17 @@ NDArray* al_comm_reduce(int redop, const NDArray* shard, const size_t* dims, siz
     NDArray* part = reduce_impl(redop, shard, dims, ndims, 0.0f, false);
     if (!part) return nullptr;
     const ncclRedOp_t ops[AL_REDOP_COUNT] = {ncclSum, ncclMax, ncclMin, ncclProd};
+    if (scatter) {
+        NDArray* out = new_array(lshape, nd);
+        bool ok = out && nccl_ok(g_nccl.ReduceScatter(part->ptr, out->ptr, nout / g_nccl.world, ncclFloat32, ops[redop], g_nccl.comm, rt().stream), "ncclReduceScatter");
+        std::string keep = last_error_string();
+        array_free(part);
+        if (!ok && out) array_free(out);
+        restore_error(keep);
+        if (!ok) return nullptr;
+        note_launch("nccl_reduce_scatter");
+        return out;
+    }
     if (!nccl_ok(g_nccl.AllReduce(part->ptr, part->ptr, nout, ncclFloat32, ops[redop], g_nccl.comm, rt().stream), "ncclAllReduce")) {
         std::string keep = last_error_string();
         array_free(part);
@@ -515,6 +581,39 @@ NDArray* al_comm_reduce(int redop, const NDArray* shard, const size_t* dims, siz
     }
     note_launch("nccl_allreduce");
     return part;
+}
+
+// Result REPLICATED on every rank (allreduce semantics).
+NDArray* al_comm_reduce(int redop, const NDArray* shard, const size_t* dims, size_t ndims) {
+    AL_ENTER;
+    return comm_reduce(redop, shard, dims, ndims, 0, false);
+}
+
+// Result SHARDED along its leading non-reduced axis (reduce-scatter semantics): rank r gets block r.
+NDArray* al_comm_reduce_scatter(int redop, const NDArray* shard, const size_t* dims, size_t ndims) {
+    AL_ENTER;
+    return comm_reduce(redop, shard, dims, ndims, 0, true);
+}
+
+// Both of the above for a shard that is cut along `shard_axis` (all axes before it have extent 1).
+NDArray* al_comm_reduce_ex(int redop, const NDArray* shard, const size_t* dims, size_t ndims, size_t shard_axis, int scatter) {
+    AL_ENTER;
+    return comm_reduce(redop, shard, dims, ndims, shard_axis, scatter != 0);
+}
+
+// 1 when al_comm_reduce_scatter can shard the result of reducing `dims` of an array of this shape.
+int al_comm_can_scatter(const size_t* shape, size_t nd, const size_t* dims, size_t ndims) {
+    AL_ENTER;
+    if (!g_nccl.comm || g_nccl.world == 1 || nd == 0 || nd > 64) return 0;
+    size_t dshape[64], ax;
+    bool crosses = false;
+    for (size_t i = 0; i < nd; i++) dshape[i] = shape[i];
+    for (size_t i = 0; i < ndims; i++) {
+        if (dims[i] >= nd) return 0;
+        dshape[dims[i]] = 1;
+        crosses |= dims[i] == 0;
+    }
+    return crosses && scatter_axis(dshape, nd, g_nccl.world, &ax) ? 1 : 0;
 }
 
 const char* al_comm_transport(void) {

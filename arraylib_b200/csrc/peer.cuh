@@ -32,6 +32,7 @@ struct PeerMap {
     FastDiv segdiv;
     uint32_t seg;  // elements per segment, a multiple of 4 (a float4 never straddles two owners)
     int world;     // 0: no peer target, store locally
+    int rank;      // this rank (the fused kernels start their walk at their own segment, see reduce_outer)
 };
 __device__ __forceinline__ float* peer_dst(const PeerMap& m, uint32_t e) {
     const uint32_t o = fdiv(e, m.segdiv);
@@ -42,7 +43,7 @@ __device__ __forceinline__ float* peer_dst(const PeerMap& m, uint32_t e) {
 bool peer_available();                           // communicator up and the IPC windows mapped
 bool peer_begin(uint64_t nout, PeerMap* map);    // grow the windows if needed (collective) and fill `map`
 bool peer_push(const float* partial, uint64_t nout, const PeerMap& map);  // step 1 for an already materialised partial
-bool peer_finish(int redop, float* out, uint64_t nout, float init);        // steps 2 and 3
+bool peer_finish(int redop, float* out, uint64_t nout, float init, bool scatter);  // steps 2 and 3 (scatter: step 2 only, own segment -> out)
 // local reduce with the peer epilogue (reduce.cu); *used = false when the chosen plan has none
 bool reduce_into_peers(int redop, const NDArray* src, const size_t* dims, size_t ndims, const PeerMap& map, bool* used);
 

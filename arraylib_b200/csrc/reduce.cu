@@ -74,6 +74,7 @@ struct RedArgs {
     float init;
     int finalize;
     PeerMap peer;        // world > 0: final stores go to the owners' peer slots, un-finalised (peer.cuh)
+    uint32_t rot;        // reduce_outer: CTA x-index rotation (rank * gridDim.x / world when storing to peers)
 };
 
 __device__ __forceinline__ long long kept_offset(const RedArgs& a, uint32_t g) {
@@ -152,7 +153,11 @@ template <int OP, int VEC>
 __global__ void __launch_bounds__(256) reduce_outer_kernel(const RedArgs a) {
     extern __shared__ float4 smem_raw[];
     Acc<VEC>* sm = reinterpret_cast<Acc<VEC>*>(smem_raw);
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    // With a peer epilogue every rank starts at its OWN output segment and walks round from there, so that at any
+    // moment the ranks store to different owners (no NVLink incast on one GPU).
+    uint32_t bx = blockIdx.x + a.rot;
+    if (bx >= gridDim.x) bx -= gridDim.x;
+    const uint32_t g = bx * blockDim.x + threadIdx.x;
     const bool live = g < a.nk_items;
     const uint32_t r0 = blockIdx.y * a.r_per_split;
     const uint32_t r1 = min(r0 + a.r_per_split, a.nr_items);
@@ -839,6 +844,176 @@ reduce_window_any_kernel(const float* __restrict__ x, float* __restrict__ out, u
     }
 }
 
+// Register/shuffle variant (default for w = 8/16/32/64/128 when source and output rows are 16-byte aligned;
+// config C5a). The kernels above push every element through shared memory six times (stage, read, P and
+// S write, two output reads): ~8 LSU operations per output on a pipe that saturates at SM-clock rate, so
+// under a power cap (lower SM clock) they fall below the HBM roofline (ncu: L1/TEX 83 %, DRAM 75 %). Here
+// nothing touches shared memory and there is no block barrier:
+//   * a warp owns R consecutive "rows" of 128 source elements; lane l holds elements 4l..4l+3 of a row as
+//     ONE 128-bit load, so a block of w elements is G = w/4 adjacent lanes;
+//   * lane-local prefix/suffix sums (6 adds), then the block-wide EXCLUSIVE prefix E and suffix F of the
+//     lane totals by Kogge-Stone over the G lanes: log2(G) shfl.up + log2(G) shfl.down with predicated adds; four
+//     rows are scanned together so that their (independent) shuffle chains hide each other's latency;
+//   * out[k] = S[b][k] (+) Pex[b+1][k]: the exclusive prefix of the NEXT block lives G lanes to the right
+//     (in the next row for the last block of a row), fetched with 4 index shuffles per row; the publisher
+//     selects which row it publishes, so one shuffle serves both cases;
+//   * results leave as one 128-bit store per lane.
+// Per 128 outputs: 1 LDG.128 + 1 STG.128 + 2*log2(G)+4 SHFL (12 for w = 64) and ~40 FADD -- about a third of
+// the LSU work of the shared-memory kernels. Loads are double buffered in registers (B rows in flight while
+// B rows are being scanned). Each segment of R = B*NB-1 output rows re-scans one halo row (only its first G
+// lanes load anything).
+constexpr int kShflThreads = 128;
+
+template <int OP, int W, int B, int NB>
+__global__ void __launch_bounds__(kShflThreads, 4)
+reduce_window_shfl_kernel(const float* __restrict__ x, float* __restrict__ out, uint32_t nout, uint32_t n_segs,
+                          uint32_t segs_per_row, long long row_stride, float init, int init_is_identity) {
+    constexpr int G = W / 4;         // lanes per block of W elements
+    constexpr int R = B * NB - 1;    // output rows (of 128) per segment; the last loaded row is the halo
+    constexpr int IL = 4;            // rows scanned together: their shuffle chains are independent and interleave
+    constexpr int STEPS = G == 2 ? 1 : G == 4 ? 2 : G == 8 ? 3 : G == 16 ? 4 : 5;
+    static_assert(G >= 2 && G <= 32 && (G & (G - 1)) == 0 && B % IL == 0, "w/4 must be a power of two up to 32");
+    constexpr int WPC = kShflThreads / 32;
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = blockIdx.x * WPC + (threadIdx.x >> 5), nw = gridDim.x * WPC;
+    const uint32_t n_in = nout + W - 1;  // < 2^31 + 128: element indices inside a signal fit 32 bits
+    const bool ident = init_is_identity != 0;
+    const float id = rident<OP>();
+    const int partner = (lane + G) & 31;
+    const bool low = lane < G;  // this lane's consumer sits in the PREVIOUS row
+    bool pu[STEPS], pd[STEPS];  // does the Kogge-Stone source lane of step k lie inside this lane's block?
+#pragma unroll
+    for (int k = 0; k < STEPS; k++) {
+        pu[k] = (lane & (G - 1)) >= (1 << k);
+        pd[k] = (lane & (G - 1)) + (1 << k) < G;
+    }
+
+    if (gw >= n_segs) return;
+    const uint32_t n_it = ((n_segs - gw + nw - 1) / nw) * NB;  // batches this warp walks through
+
+    float4 nxt[B];
+    auto fetch = [&](uint32_t it) {
+        const uint32_t seg = gw + (it / NB) * nw;
+        const uint32_t batch = it % NB;
+        const uint32_t row = seg / segs_per_row;
+        const uint32_t e0 = ((seg - row * segs_per_row) * R + batch * B) * 128;  // first element of the batch
+        const float* src = x + (long long)row * row_stride + e0 + 4 * lane;
+        const bool halo_idle = batch == NB - 1 && !low;  // last row of the segment: only the first block is needed
+        if (e0 + B * 128 <= n_in) {  // warp-uniform: whole batch in range
+#pragma unroll
+            for (int u = 0; u < B; u++) {
+                if (u == B - 1 && halo_idle) nxt[u] = make_float4(id, id, id, id);
+                else nxt[u] = __ldcs(reinterpret_cast<const float4*>(src + u * 128));
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < B; u++) {
+                const uint32_t e = e0 + u * 128 + 4 * lane;
+                const bool skip = u == B - 1 && halo_idle;
+                nxt[u].x = (!skip && e + 0 < n_in) ? __ldcs(src + u * 128 + 0) : id;
+                nxt[u].y = (!skip && e + 1 < n_in) ? __ldcs(src + u * 128 + 1) : id;
+                nxt[u].z = (!skip && e + 2 < n_in) ? __ldcs(src + u * 128 + 2) : id;
+                nxt[u].w = (!skip && e + 3 < n_in) ? __ldcs(src + u * 128 + 3) : id;
+            }
+        }
+    };
+
+    fetch(0);
+    float cs0 = id, cs1 = id, cs2 = id, cs3 = id, cx0 = id, cx1 = id, cx2 = id, cx3 = id;
+    for (uint32_t it = 0; it < n_it; it++) {
+        float4 cur[B];
+#pragma unroll
+        for (int u = 0; u < B; u++) cur[u] = nxt[u];
+        if (it + 1 < n_it) fetch(it + 1);
+        const uint32_t seg = gw + (it / NB) * nw;
+        const uint32_t batch = it % NB;
+        const uint32_t row = seg / segs_per_row;
+        const uint32_t r0 = (seg - row * segs_per_row) * R + batch * B;  // 128-element row index of cur[0]
+        float* const dst = out + (size_t)row * nout + 4 * lane;
+        const bool all_full = (r0 + B - 1) * 128 <= nout;  // every row emitted by this batch is a whole row
+#pragma unroll
+        for (int g = 0; g < B; g += IL) {
+            float p2[IL], p3[IL], s0[IL], s1[IL], s2[IL], vu[IL], vd[IL], E[IL], F[IL];
+#pragma unroll
+            for (int i = 0; i < IL; i++) {
+                const float4 xv = cur[g + i];
+                p2[i] = racc<OP>(xv.x, xv.y), p3[i] = racc<OP>(p2[i], xv.z);
+                s2[i] = racc<OP>(xv.z, xv.w), s1[i] = racc<OP>(xv.y, s2[i]), s0[i] = racc<OP>(xv.x, s1[i]);
+                vu[i] = vd[i] = racc<OP>(p3[i], xv.w);
+                E[i] = F[i] = id;
+            }
+            // exclusive prefix E / suffix F of the lane totals inside each block of G lanes (Kogge-Stone; the
+            // inclusive values vu / vd only feed the next step)
+#pragma unroll
+            for (int k = 0; k < STEPS; k++) {
+                float ou[IL], od[IL];
+#pragma unroll
+                for (int i = 0; i < IL; i++) {
+                    ou[i] = __shfl_up_sync(0xffffffffu, vu[i], 1 << k, G);
+                    od[i] = __shfl_down_sync(0xffffffffu, vd[i], 1 << k, G);
+                }
+#pragma unroll
+                for (int i = 0; i < IL; i++) {
+                    if (pu[k]) vu[i] = racc<OP>(ou[i], vu[i]), E[i] = racc<OP>(ou[i], E[i]);
+                    if (pd[k]) vd[i] = racc<OP>(vd[i], od[i]), F[i] = racc<OP>(F[i], od[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < IL; i++) {
+                const float4 xv = cur[g + i];
+                const float nx0 = E[i], nx1 = racc<OP>(E[i], xv.x), nx2 = racc<OP>(E[i], p2[i]), nx3 = racc<OP>(E[i], p3[i]);
+                if (g + i > 0 || batch > 0) {  // emit the previous row: its own suffixes (+) the next block's exclusive prefixes
+                    float4 o;
+                    if constexpr (G == 32) {
+                        o.x = nx0, o.y = nx1, o.z = nx2, o.w = nx3;
+                    } else {
+                        o.x = __shfl_sync(0xffffffffu, low ? nx0 : cx0, partner);
+                        o.y = __shfl_sync(0xffffffffu, low ? nx1 : cx1, partner);
+                        o.z = __shfl_sync(0xffffffffu, low ? nx2 : cx2, partner);
+                        o.w = __shfl_sync(0xffffffffu, low ? nx3 : cx3, partner);
+                    }
+                    o.x = racc<OP>(cs0, o.x), o.y = racc<OP>(cs1, o.y), o.z = racc<OP>(cs2, o.z), o.w = racc<OP>(cs3, o.w);
+                    if (!ident) {  // with the identity as init the fold changes nothing: no sum here is -0, no max/min is NaN
+                        o.x = rfinal<OP>(init, o.x), o.y = rfinal<OP>(init, o.y), o.z = rfinal<OP>(init, o.z), o.w = rfinal<OP>(init, o.w);
+                    }
+                    const uint32_t e = (r0 + g + i - 1) * 128;  // first output of the row being emitted
+                    if (all_full || e + 128 <= nout) {
+                        __stcs(reinterpret_cast<float4*>(dst + e), o);
+                    } else {
+                        const uint32_t el = e + 4 * lane;
+                        if (el + 0 < nout) __stcs(dst + e + 0, o.x);
+                        if (el + 1 < nout) __stcs(dst + e + 1, o.y);
+                        if (el + 2 < nout) __stcs(dst + e + 2, o.z);
+                        if (el + 3 < nout) __stcs(dst + e + 3, o.w);
+                    }
+                }
+                cs0 = racc<OP>(s0[i], F[i]), cs1 = racc<OP>(s1[i], F[i]), cs2 = racc<OP>(s2[i], F[i]), cs3 = racc<OP>(xv.w, F[i]);
+                cx0 = nx0, cx1 = nx1, cx2 = nx2, cx3 = nx3;
+            }
+        }
+    }
+}
+
+template <int OP, int W>
+static bool launch_window_shfl(const float* src, float* out, uint32_t nout, uint32_t rows, long long row_stride, float init) {
+    const float ident_tab[AL_REDOP_COUNT] = {0.0f, -INFINITY, INFINITY, 1.0f};
+    const int init_is_identity = memcmp(&init, &ident_tab[OP], sizeof(float)) == 0;
+    const long variant = rt().window_shfl;  // 1: 8 rows x 4 batches per segment, 2: 4 rows x 8 batches
+    const uint64_t rows128 = ((uint64_t)nout + 127) / 128;
+    const uint64_t segs_per_row = (rows128 + 30) / 31;  // both variants: R = 31
+    const uint64_t all_segs = segs_per_row * rows;
+    if (all_segs >= (1ull << 31)) return set_error("NotImplementedError: too many window segments"), false;
+    const long per_sm = rt().window_ctas_per_sm > 0 ? rt().window_ctas_per_sm : 4;
+    uint64_t blocks = (all_segs + 3) / 4;
+    if (blocks > (uint64_t)kNumSMs * per_sm) blocks = (uint64_t)kNumSMs * per_sm;
+    if (variant == 2)
+        reduce_window_shfl_kernel<OP, W, 4, 8><<<(unsigned)blocks, kShflThreads, 0, rt().stream>>>(src, out, nout, (uint32_t)all_segs, (uint32_t)segs_per_row, row_stride, init, init_is_identity);
+    else
+        reduce_window_shfl_kernel<OP, W, 8, 4><<<(unsigned)blocks, kShflThreads, 0, rt().stream>>>(src, out, nout, (uint32_t)all_segs, (uint32_t)segs_per_row, row_stride, init, init_is_identity);
+    note_launch("reduce_window_shfl");
+    return check_launch("reduce_window_shfl");
+}
+
 template <int OP, int W>
 static bool launch_window_fixed(const float* src, float* out, uint32_t nout, uint32_t rows, long long row_stride, float init) {
     const float ident_tab[AL_REDOP_COUNT] = {0.0f, -INFINITY, INFINITY, 1.0f};
@@ -974,6 +1149,19 @@ static bool run_reduce(const float* src, float* out, const AxisList& K, const Ax
         const uint32_t per_row = (uint32_t)K.extent[0];
         const uint32_t rows = K.n == 2 ? (uint32_t)K.extent[1] : 1;
         const long long row_stride = K.n == 2 ? K.stride[1] : 0;
+        // 128-bit rows on both sides: the register/shuffle kernel (no shared memory)
+        const bool rows_aligned = (uintptr_t)src % 16 == 0 && (uintptr_t)out % 16 == 0 &&
+                                  (rows == 1 || (per_row % 4 == 0 && row_stride % 4 == 0));
+        if (r.window_shfl && rows_aligned) {
+            switch (w) {
+                case 8: return launch_window_shfl<OP, 8>(src, out, per_row, rows, row_stride, init);
+                case 16: return launch_window_shfl<OP, 16>(src, out, per_row, rows, row_stride, init);
+                case 32: return launch_window_shfl<OP, 32>(src, out, per_row, rows, row_stride, init);
+                case 64: return launch_window_shfl<OP, 64>(src, out, per_row, rows, row_stride, init);
+                case 128: return launch_window_shfl<OP, 128>(src, out, per_row, rows, row_stride, init);
+                default: break;
+            }
+        }
         switch (w) {
             case 8: return launch_window_fixed<OP, 8>(src, out, per_row, rows, row_stride, init);
             case 16: return launch_window_fixed<OP, 16>(src, out, per_row, rows, row_stride, init);
@@ -1058,7 +1246,10 @@ static bool run_reduce(const float* src, float* out, const AxisList& K, const Ax
             if (peer) finish_peer = *peer;
         } else {
             a.dst = out;
-            if (peer) a.peer = *peer;
+            if (peer) {
+                a.peer = *peer;
+                a.rot = (uint32_t)(((uint64_t)peer->rank * gx) / (uint64_t)peer->world);
+            }
         }
         if (peer) *peer_used = true;
         size_t smem = TY > 1 ? (size_t)256 * sizeof(float) * VEC : 0;

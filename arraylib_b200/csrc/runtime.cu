@@ -409,6 +409,7 @@ int al_set_tuning(const char* key, long value) {
     else if (k == "reduce_sequential") g_rt.reduce_sequential = value;
     else if (k == "reduce_loads_per_lane") g_rt.reduce_loads_per_lane = value;
     else if (k == "disable_window") g_rt.disable_window = value;
+    else if (k == "window_shfl") g_rt.window_shfl = value;
     else if (k == "window_ctas_per_sm") g_rt.window_ctas_per_sm = value;
     else if (k == "window_whole_blocks") g_rt.window_whole_blocks = value;
     else if (k == "tile64") g_rt.tile64 = value;

@@ -245,6 +245,14 @@ int al_comm_alltoall(const NDArray* send, NDArray* recv);   /* block r of send -
  * rank. One node: the local reduce kernel stores into CUDA-IPC peer windows over NVLink and the partials are
  * combined in rank order (deterministic); otherwise local reduce + ncclAllReduce. Collective call. */
 NDArray* al_comm_reduce(int redop, const NDArray* shard, const size_t* reduce_dims, size_t reduce_ndim);
+/* The same reduction with the result left SHARDED along its leading non-reduced axis (first axis whose keepdims
+ * extent is > 1), rank r receiving block r: the peer-memory path then needs one hand-over and no result broadcast
+ * (reduce-scatter). Needs that extent to be a multiple of the world size and 16-byte aligned blocks;
+ * al_comm_can_scatter answers whether a (shape, dims) pair qualifies. Collective call. */
+NDArray* al_comm_reduce_scatter(int redop, const NDArray* shard, const size_t* reduce_dims, size_t reduce_ndim);
+/* both variants for a shard cut along `shard_axis` (every axis before it has extent 1) */
+NDArray* al_comm_reduce_ex(int redop, const NDArray* shard, const size_t* reduce_dims, size_t reduce_ndim, size_t shard_axis, int scatter);
+int al_comm_can_scatter(const size_t* shape, size_t ndim, const size_t* reduce_dims, size_t reduce_ndim);
 const char* al_comm_transport(void);                        /* "peer-memory" | "nccl (<why>)" | "single process" */
 int al_comm_destroy(void);
 

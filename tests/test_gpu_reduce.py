@@ -141,7 +141,7 @@ def test_batched_sliding_windows(al, orc, rng, rows, n, w):
     V = al.from_numpy(base.reshape(-1)).as_strided(shape=(rows, n - w + 1, w), stride=(n, 1, 1))
     vn = np.lib.stride_tricks.as_strided(base, shape=(rows, n - w + 1, w), strides=(4 * n, 4, 4))
     got = al.reduce_sum(V, dims=[2])
-    assert lib.al_last_kernel() == b"reduce_window"
+    assert lib.al_last_kernel() == b"reduce_window"  # output rows of n-w+1 floats are not 16-byte aligned: shared-memory kernel
     assert got.shape == (rows, n - w + 1, 1)
     assert_bit_equal(al.to_numpy(got), orc.reduce("sum", vn, (2,)), "batched windows")
     assert_bit_equal(al.to_numpy(al.reduce_min(V, dims=[2])), orc.reduce("min", vn, (2,)), "batched windows min")
@@ -152,33 +152,88 @@ def test_window_kernel_matches_generic_path(al, rng):
     base = rng.standard_normal(50000).astype(np.float32)
     V = al.from_numpy(base).as_strided(shape=(50000 - 63, 64), stride=(1, 1))
     fast = al.to_numpy(al.reduce_max(V, dims=[1]))
-    assert lib.al_last_kernel() == b"reduce_window"
+    assert lib.al_last_kernel() == b"reduce_window_shfl"
     lib.al_set_tuning(b"disable_window", 1)
     try:
         slow = al.to_numpy(al.reduce_max(V, dims=[1]))
-        assert lib.al_last_kernel() != b"reduce_window"
+        assert not lib.al_last_kernel().startswith(b"reduce_window")
     finally:
         lib.al_set_tuning(b"disable_window", 0)
     assert_bit_equal(fast, slow, "window vs generic")
 
 
-@pytest.mark.parametrize("w", [8, 16, 32, 64])
-def test_window_half_block_and_whole_block_kernels_agree(al, orc, rng, w):
+@pytest.mark.parametrize("w", [8, 16, 32, 64, 128])
+def test_window_kernel_variants_agree(al, orc, rng, w):
+    """The register/shuffle kernel (both row groupings) and the two shared-memory kernels against the oracle,
+    with a stretch of all-NaN windows (max/min must give the identity like the reference)."""
     from arraylib_b200._lib import lib
     n = 300000
     base = int_data(rng, (n,))
-    base[1000:1100] = np.nan  # a stretch of all-NaN windows: max/min must give the identity like the reference
+    base[1000:1100 + w] = np.nan
     V = al.from_numpy(base).as_strided(shape=(n - w + 1, w), stride=(1, 1))
     vn = np.lib.stride_tricks.as_strided(base, shape=(n - w + 1, w), strides=(4, 4))
     for op in ("sum", "max", "min"):
         want = orc.reduce(op, vn, (1,))
-        for whole in (0, 1):
+        for shfl, whole, name in ((1, 0, b"reduce_window_shfl"), (2, 0, b"reduce_window_shfl"), (0, 0, b"reduce_window"), (0, 1, b"reduce_window")):
+            lib.al_set_tuning(b"window_shfl", shfl)
             lib.al_set_tuning(b"window_whole_blocks", whole)
             try:
                 got = al.to_numpy(getattr(al, f"reduce_{op}")(V, dims=[1]))
+                if w <= 64 or shfl:
+                    assert lib.al_last_kernel() == name
             finally:
+                lib.al_set_tuning(b"window_shfl", 1)
                 lib.al_set_tuning(b"window_whole_blocks", 0)
-            assert_bit_equal(got, want, f"{op} whole_blocks={whole}")
+            assert_bit_equal(got, want, f"{op} shfl={shfl} whole_blocks={whole}")
+
+
+@pytest.mark.parametrize("w", [8, 16, 32, 64, 128])
+@pytest.mark.parametrize("nout", [4, 124, 128, 132, 31 * 128 - 4, 31 * 128, 31 * 128 + 4, 62 * 128 + 8, 1000003])
+def test_shuffle_window_kernel_edges(al, orc, rng, w, nout):
+    """Segment / row / vector boundaries of the register/shuffle kernel: outputs per signal just below, at and just above
+    a 128-output row and a 31-row segment, odd lengths (scalar tail stores, partial last vector of the source), a
+    custom init, and float data against the stated tolerance."""
+    from arraylib_b200._lib import lib
+    n = nout + w - 1
+    if nout < 4 * w:
+        pytest.skip("windows this short take the generic path")
+    base = int_data(rng, (n,))
+    B = al.from_numpy(base)
+    V = B.as_strided(shape=(nout, w), stride=(1, 1))
+    vn = np.lib.stride_tricks.as_strided(base, shape=(nout, w), strides=(4, 4))
+    for op in ("sum", "max", "min"):
+        got = getattr(al, f"reduce_{op}")(V, dims=[1])
+        assert lib.al_last_kernel() == b"reduce_window_shfl"
+        assert_bit_equal(al.to_numpy(got), orc.reduce(op, vn, (1,)), f"{op} w={w} nout={nout}")
+    got = al.reduce(lambda a, b: a + b, V, dims=[1], init=3.0)
+    assert_bit_equal(al.to_numpy(got), orc.reduce("sum", vn, (1,), init=3.0), "custom init")
+    f = rng.standard_normal(n).astype(np.float32)
+    F = al.from_numpy(f).as_strided(shape=(nout, w), stride=(1, 1))
+    fn_ = np.lib.stride_tricks.as_strided(f, shape=(nout, w), strides=(4, 4))
+    err = np.abs(al.to_numpy(al.reduce_sum(F, dims=[1])).astype(np.float64) - orc.reduce("sum", fn_, (1,)))
+    assert np.all(err <= sum_tolerance(fn_, (1,)))
+
+
+@pytest.mark.parametrize("rows,nout,w", [(3, 4000, 64), (7, 128 * 31, 16), (2, 40000, 128), (5, 516, 8)])
+def test_batched_windows_with_aligned_rows_use_the_shuffle_kernel(al, orc, rng, rows, nout, w):
+    """Signals stored with a padded pitch (row stride and outputs per row both multiples of 4): the register/shuffle
+    kernel takes batches too. Also a misaligned base pointer, which must fall back to the shared-memory kernel."""
+    from arraylib_b200._lib import lib
+    pitch = (nout + w - 1 + 3) // 4 * 4
+    base = int_data(rng, (rows * pitch + 8,))
+    B = al.from_numpy(base)
+    V = B.as_strided(shape=(rows, nout, w), stride=(pitch, 1, 1))
+    vn = np.lib.stride_tricks.as_strided(base, shape=(rows, nout, w), strides=(4 * pitch, 4, 4))
+    for op in ("sum", "min"):
+        got = getattr(al, f"reduce_{op}")(V, dims=[2])
+        assert lib.al_last_kernel() == b"reduce_window_shfl"
+        assert_bit_equal(al.to_numpy(got), orc.reduce(op, vn, (2,)), f"batched {op}")
+    off = B[1:rows * pitch + 8]  # base pointer 4 bytes past a 16-byte boundary
+    V1 = off.as_strided(shape=(rows, nout, w), stride=(pitch, 1, 1))
+    v1 = np.lib.stride_tricks.as_strided(base[1:], shape=(rows, nout, w), strides=(4 * pitch, 4, 4))
+    got = al.reduce_sum(V1, dims=[2])
+    assert lib.al_last_kernel() in (b"reduce_window", b"reduce_window_any")
+    assert_bit_equal(al.to_numpy(got), orc.reduce("sum", v1, (2,)), "misaligned base")
 
 
 @pytest.mark.parametrize("splits", [1, 2, 7, 64])

@@ -108,20 +108,100 @@ def bench_transpose():
 def bench_window():
     n, w = 1 << 28, 64
     base = rnd((n,), 1)
-    for per_sm in (8, 16, 32):
-        tune(window_ctas_per_sm=per_sm)
-        timed(lambda: base.as_strided(shape=(n - w + 1, w), stride=(1, 1)).reduce_sum(dims=[1]), 4 * n + 4 * (n - w + 1), f"window-64 reduce_sum 2^28 ctas/SM={per_sm}")
-    tune(window_ctas_per_sm=0, window_whole_blocks=1)
-    timed(lambda: base.as_strided(shape=(n - w + 1, w), stride=(1, 1)).reduce_sum(dims=[1]), 4 * n + 4 * (n - w + 1), "window-64 reduce_sum 2^28 whole-block kernel")
-    tune(window_whole_blocks=0)
-    timed(lambda: base.as_strided(shape=(n - w + 1, w), stride=(1, 1)).reduce_max(dims=[1]), 4 * n + 4 * (n - w + 1), "window-64 reduce_max 2^28")
-    for w2 in (8, 16, 32, 24, 100, 500):
-        timed(lambda: base.as_strided(shape=(n - w2 + 1, w2), stride=(1, 1)).reduce_sum(dims=[1]), 4 * n + 4 * (n - w2 + 1), f"window-{w2} reduce_sum 2^28", reps=3)
+    win = lambda ww: base.as_strided(shape=(n - ww + 1, ww), stride=(1, 1))  # noqa: E731
+    for variant in (1, 2):
+        for per_sm in (0, 3, 4, 5, 6, 8):
+            tune(window_shfl=variant, window_ctas_per_sm=per_sm)
+            timed(lambda: win(w).reduce_sum(dims=[1]), 4 * n + 4 * (n - w + 1), f"window-64 reduce_sum 2^28 shfl variant={variant} ctas/SM={per_sm or 'default'}")
+    tune(window_shfl=0, window_ctas_per_sm=0)
+    timed(lambda: win(w).reduce_sum(dims=[1]), 4 * n + 4 * (n - w + 1), "window-64 reduce_sum 2^28 shared-memory half-block kernel")
+    tune(window_shfl=1)
+    timed(lambda: win(w).reduce_max(dims=[1]), 4 * n + 4 * (n - w + 1), "window-64 reduce_max 2^28")
+    for w2 in (8, 16, 32, 128, 24, 100, 500):
+        for variant in (1, 0):
+            tune(window_shfl=variant)
+            timed(lambda: win(w2).reduce_sum(dims=[1]), 4 * n + 4 * (n - w2 + 1), f"window-{w2} reduce_sum 2^28 shfl={variant}", reps=3)
+    tune(window_shfl=1)
     n2 = 1 << 24
     b2 = rnd((n2,), 1)
     tune(disable_window=1)
     timed(lambda: b2.as_strided(shape=(n2 - w + 1, w), stride=(1, 1)).reduce_sum(dims=[1]), 8 * n2, "window-64 reduce_sum 2^24 generic path", reps=3)
     tune(disable_window=0)
+
+
+def smi_clock():
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-i", "0"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+    except Exception as exc:  # noqa: BLE001
+        out = repr(exc)
+    return out
+
+
+def bench_c5a_attrib():
+    """Why is C5a slower inside the suite than alone? Time it after an idle gap, after a read-heavy op, after a
+    write-heavy op and inside a long busy stretch, logging SM clock / power around each measurement."""
+    import threading
+    import time
+    n, w = 1 << 28, 64
+    base = rnd((n,), 1)
+    X = rnd((64, 512, 512, 64), 2)
+    a, b = rnd((n,), 3), rnd((n,), 4)
+    c5a = lambda: base.as_strided(shape=(n - w + 1, w), stride=(1, 1)).reduce_sum(dims=[1])  # noqa: E731
+    nbytes = 4 * n + 4 * (n - w + 1)
+    samples, stop = [], threading.Event()
+
+    def sampler():
+        while not stop.is_set():
+            samples.append((time.perf_counter(), smi_clock()))
+            time.sleep(0.05)
+
+    def one(label, before=None, reps=5):
+        ts = []
+        for _ in range(reps):
+            if before:
+                r0 = before()
+                del r0
+            lib.al_event_record(0)
+            r = c5a()
+            lib.al_event_record(1)
+            ms = C.c_float()
+            assert lib.al_event_elapsed(0, 1, C.byref(ms)) == 0
+            ts.append(ms.value)
+            del r
+        print(f"{label:64s} median {statistics.median(ts):.4f} ms = {nbytes / statistics.median(ts) / 1e6:7.1f} GB/s  all {[round(t, 4) for t in ts]}  [{lib.al_last_kernel().decode()}] smi: {smi_clock()}", flush=True)
+
+    for variant in (1, 0):
+        tune(window_shfl=variant)
+        print(f"--- window_shfl={variant}", flush=True)
+        for _ in range(3):
+            r = c5a()
+            del r
+        al.synchronize()
+        time.sleep(2.0)
+        one("after a 2 s idle gap (first = cold clocks)")
+        one("back to back")
+        one("after reduce_sum(X, dims=(3,)) [read-heavy 4 GiB]", lambda: X.reduce_sum(dims=(3,)))
+        one("after reduce_sum(X, dims=(0,)) [64 MiB output left dirty in L2]", lambda: X.reduce_sum(dims=(0,)))
+        one("after a+b [1 GiB written]", lambda: a + b)
+        th = threading.Thread(target=sampler, daemon=True)
+        th.start()
+        t_end = time.perf_counter() + 4.0
+        while time.perf_counter() < t_end:   # long busy stretch: the power cap, if any, sets in here
+            for _ in range(20):
+                r = a + b
+                del r
+                r = X.reduce_sum(dims=(0,))
+                del r
+            al.synchronize()
+        one("inside a 4 s busy stretch (after reduce dims=(0,))", lambda: X.reduce_sum(dims=(0,)), reps=9)
+        stop.set()
+        th.join()
+        stop.clear()
+        print("   smi during the busy stretch (sm MHz, W, sw_power_cap):", [s for _, s in samples[:: max(len(samples) // 12, 1)]], flush=True)
+        samples.clear()
+    tune(window_shfl=1)
 
 
 def bench_reduce():
