@@ -41,7 +41,7 @@ struct Runtime {
     long reduce_sequential = 0;  // 1: one thread per output, the reference's summation order (bit-exact, slow)
     long disable_window = 0;
     long window_whole_blocks = 0;  // 1: fixed-w windows use the whole-block scan kernel instead of the half-block one
-    long window_shfl = 1;      // fixed-w windows: 1/2 = register/shuffle kernel (8x4 / 4x8 rows per segment), 0 = shared-memory kernels
+    long window_shfl = 1;      // fixed-w windows: 1..4 = register/shuffle kernel (cp.async ring shapes), 0 = shared-memory scan kernels
     long window_ctas_per_sm = 0;  // 0 = default (32 CTAs per SM, 4 of them resident)
     long tile64 = 1;           // 0: use the 32x32 scalar transpose tile even when the float4 one applies
     long tile_tq = 64;         // q extent of the 128-bit transpose tile: 32, 64 or 128 (p extent = 4096 / tq)

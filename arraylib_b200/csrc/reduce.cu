@@ -24,6 +24,7 @@
 // Summation order differs from the reference (tree instead of sequential), so reduce_sum carries
 // the tolerance stated in DESIGN.md; max/min are order independent.
 #include <algorithm>
+#include <type_traits>
 
 #include "al_internal.h"
 #include "device_utils.cuh"
@@ -862,20 +863,32 @@ reduce_window_any_kernel(const float* __restrict__ x, float* __restrict__ out, u
 // the LSU work of the shared-memory kernels. Loads are double buffered in registers (B rows in flight while
 // B rows are being scanned). Each segment of R = B*NB-1 output rows re-scans one halo row (only its first G
 // lanes load anything).
-constexpr int kShflThreads = 128;
 
-template <int OP, int W, int B, int NB>
-__global__ void __launch_bounds__(kShflThreads, 4)
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
+    // 16 bytes global -> shared without passing through registers; bytes beyond src_bytes are zero-filled and not read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// B rows per batch, S batches per warp in a shared-memory ring (S - 1 of them in flight). The ring exists only to keep
+// bytes in flight WITHOUT holding registers: a register double buffer gave 64 KB per SM in flight and the warps spent
+// 39 % of their time waiting for it (ncu, round 2: DRAM 73 % busy, issue slots 50 %). Every lane reads back exactly
+// the 16-byte slots it copied itself (cp.async + wait_group is per thread), so there is no barrier, no mbarrier and no
+// cross-proxy ordering anywhere.
+template <int OP, int W, int B, int S, int NB, int WPC>
+__global__ void __launch_bounds__(WPC * 32, 512 / (WPC * 32))
 reduce_window_shfl_kernel(const float* __restrict__ x, float* __restrict__ out, uint32_t nout, uint32_t n_segs,
                           uint32_t segs_per_row, long long row_stride, float init, int init_is_identity) {
+    extern __shared__ float4 ring_raw[];
     constexpr int G = W / 4;         // lanes per block of W elements
-    constexpr int R = B * NB - 1;    // output rows (of 128) per segment; the last loaded row is the halo
+    constexpr int R = B * NB - 1;    // output rows (of 128) per segment of NB batches; the last loaded row is the halo
     constexpr int IL = 4;            // rows scanned together: their shuffle chains are independent and interleave
     constexpr int STEPS = G == 2 ? 1 : G == 4 ? 2 : G == 8 ? 3 : G == 16 ? 4 : 5;
     static_assert(G >= 2 && G <= 32 && (G & (G - 1)) == 0 && B % IL == 0, "w/4 must be a power of two up to 32");
-    constexpr int WPC = kShflThreads / 32;
-    const int lane = threadIdx.x & 31;
-    const uint32_t gw = blockIdx.x * WPC + (threadIdx.x >> 5), nw = gridDim.x * WPC;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t gw = blockIdx.x * WPC + warp, nw = gridDim.x * WPC;
     const uint32_t n_in = nout + W - 1;  // < 2^31 + 128: element indices inside a signal fit 32 bits
     const bool ident = init_is_identity != 0;
     const float id = rident<OP>();
@@ -887,131 +900,181 @@ reduce_window_shfl_kernel(const float* __restrict__ x, float* __restrict__ out, 
         pu[k] = (lane & (G - 1)) >= (1 << k);
         pd[k] = (lane & (G - 1)) + (1 << k) < G;
     }
-
     if (gw >= n_segs) return;
     const uint32_t n_it = ((n_segs - gw + nw - 1) / nw) * NB;  // batches this warp walks through
 
-    float4 nxt[B];
-    auto fetch = [&](uint32_t it) {
+    float4* const ring = ring_raw + (size_t)warp * (S * B * 32) + lane;            // [stage][row][lane]
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+
+    // first element (inside its signal) of batch `it`, and the signal it belongs to
+    auto locate = [&](uint32_t it, uint32_t& row, uint32_t& r0) {
         const uint32_t seg = gw + (it / NB) * nw;
-        const uint32_t batch = it % NB;
-        const uint32_t row = seg / segs_per_row;
-        const uint32_t e0 = ((seg - row * segs_per_row) * R + batch * B) * 128;  // first element of the batch
-        const float* src = x + (long long)row * row_stride + e0 + 4 * lane;
-        const bool halo_idle = batch == NB - 1 && !low;  // last row of the segment: only the first block is needed
-        if (e0 + B * 128 <= n_in) {  // warp-uniform: whole batch in range
+        row = segs_per_row == n_segs ? 0u : seg / segs_per_row;  // one signal (C5a): no division
+        r0 = (seg - row * segs_per_row) * R + (it % NB) * B;
+    };
+    auto issue = [&](uint32_t it) {  // batch `it` -> ring stage it % S
+        if (it < n_it) {
+            uint32_t row, r0;
+            locate(it, row, r0);
+            const uint32_t e0 = r0 * 128 + 4 * lane;  // this lane's first element
+            const float* src = x + (long long)row * row_stride + e0;
+            const uint32_t dst = ring_s + (it % S) * (B * 32 * 16);
+            const bool halo_idle = it % NB == NB - 1 && !low;  // last row of the segment: only the first block is needed
+            if ((r0 + B) * 128 <= n_in) {  // warp-uniform: the whole batch is in range
 #pragma unroll
-            for (int u = 0; u < B; u++) {
-                if (u == B - 1 && halo_idle) nxt[u] = make_float4(id, id, id, id);
-                else nxt[u] = __ldcs(reinterpret_cast<const float4*>(src + u * 128));
-            }
-        } else {
+                for (int u = 0; u < B - 1; u++) cp_async16(dst + u * (32 * 16), src + u * 128, 16u);
+                cp_async16(dst + (B - 1) * (32 * 16), halo_idle ? x : src + (B - 1) * 128, halo_idle ? 0u : 16u);
+            } else {
 #pragma unroll
-            for (int u = 0; u < B; u++) {
-                const uint32_t e = e0 + u * 128 + 4 * lane;
-                const bool skip = u == B - 1 && halo_idle;
-                nxt[u].x = (!skip && e + 0 < n_in) ? __ldcs(src + u * 128 + 0) : id;
-                nxt[u].y = (!skip && e + 1 < n_in) ? __ldcs(src + u * 128 + 1) : id;
-                nxt[u].z = (!skip && e + 2 < n_in) ? __ldcs(src + u * 128 + 2) : id;
-                nxt[u].w = (!skip && e + 3 < n_in) ? __ldcs(src + u * 128 + 3) : id;
+                for (int u = 0; u < B; u++) {
+                    const uint32_t e = e0 + u * 128;
+                    uint32_t bytes = e + 4 <= n_in ? 16u : e < n_in ? (n_in - e) * 4u : 0u;
+                    if (u == B - 1 && halo_idle) bytes = 0;
+                    cp_async16(dst + u * (32 * 16), bytes ? (const void*)(src + u * 128) : (const void*)x, bytes);
+                }
             }
         }
+        cp_async_commit();  // (an empty group when there is nothing left, so that the wait counts stay aligned)
     };
 
-    fetch(0);
+#pragma unroll
+    for (int k = 0; k < S - 1; k++) issue(k);
     float cs0 = id, cs1 = id, cs2 = id, cs3 = id, cx0 = id, cx1 = id, cx2 = id, cx3 = id;
     for (uint32_t it = 0; it < n_it; it++) {
-        float4 cur[B];
-#pragma unroll
-        for (int u = 0; u < B; u++) cur[u] = nxt[u];
-        if (it + 1 < n_it) fetch(it + 1);
-        const uint32_t seg = gw + (it / NB) * nw;
+        cp_async_wait<S - 2>();  // this lane's copies of batch `it` have landed
+        const float4* const stage = ring + (it % S) * (B * 32);
+        uint32_t row, r0;
+        locate(it, row, r0);  // r0 = 128-element row index of the batch's first row
         const uint32_t batch = it % NB;
-        const uint32_t row = seg / segs_per_row;
-        const uint32_t r0 = (seg - row * segs_per_row) * R + batch * B;  // 128-element row index of cur[0]
-        float* const dst = out + (size_t)row * nout + 4 * lane;
-        const bool all_full = (r0 + B - 1) * 128 <= nout;  // every row emitted by this batch is a whole row
+        // The stage that batch it + S - 1 lands in is the one read in the PREVIOUS iteration; those reads have been
+        // consumed by now (in-order issue), so it is free.
+        issue(it + S - 1);
+        // rows r0-1 .. r0+B-2 are emitted by this batch (row r needs the prefixes of row r+1); `drow` points at this
+        // lane's vector of row r0-1
+        float* const drow = out + (size_t)row * nout + 4 * lane + ((long long)r0 - 1) * 128;
+        const bool interior = (r0 + B - 1) * 128 <= nout && (OP == AL_RSUM || ((r0 + B) * 128 <= n_in && batch != NB - 1));
+
+        auto body = [&](auto interior_tag) {
+            constexpr bool INTERIOR = decltype(interior_tag)::value;  // whole rows everywhere, nothing to mask
 #pragma unroll
-        for (int g = 0; g < B; g += IL) {
-            float p2[IL], p3[IL], s0[IL], s1[IL], s2[IL], vu[IL], vd[IL], E[IL], F[IL];
+            for (int g = 0; g < B; g += IL) {
+                float p2[IL], p3[IL], s0[IL], s1[IL], s2[IL], vu[IL], vd[IL], E[IL], F[IL];
+                float4 cur[IL];
 #pragma unroll
-            for (int i = 0; i < IL; i++) {
-                const float4 xv = cur[g + i];
-                p2[i] = racc<OP>(xv.x, xv.y), p3[i] = racc<OP>(p2[i], xv.z);
-                s2[i] = racc<OP>(xv.z, xv.w), s1[i] = racc<OP>(xv.y, s2[i]), s0[i] = racc<OP>(xv.x, s1[i]);
-                vu[i] = vd[i] = racc<OP>(p3[i], xv.w);
-                E[i] = F[i] = id;
-            }
-            // exclusive prefix E / suffix F of the lane totals inside each block of G lanes (Kogge-Stone; the
-            // inclusive values vu / vd only feed the next step)
+                for (int i = 0; i < IL; i++) cur[i] = stage[(g + i) * 32];
+                if constexpr (!INTERIOR && OP != AL_RSUM) {  // zero fill is the identity of a sum only
 #pragma unroll
-            for (int k = 0; k < STEPS; k++) {
-                float ou[IL], od[IL];
+                    for (int i = 0; i < IL; i++) {
+                        const uint32_t e = (r0 + g + i) * 128 + 4 * lane;
+                        const bool idle = g + i == B - 1 && batch == NB - 1 && !low;
+                        if (idle || e + 0 >= n_in) cur[i].x = id;
+                        if (idle || e + 1 >= n_in) cur[i].y = id;
+                        if (idle || e + 2 >= n_in) cur[i].z = id;
+                        if (idle || e + 3 >= n_in) cur[i].w = id;
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < IL; i++) {
-                    ou[i] = __shfl_up_sync(0xffffffffu, vu[i], 1 << k, G);
-                    od[i] = __shfl_down_sync(0xffffffffu, vd[i], 1 << k, G);
+                    const float4 xv = cur[i];
+                    p2[i] = racc<OP>(xv.x, xv.y), p3[i] = racc<OP>(p2[i], xv.z);
+                    s2[i] = racc<OP>(xv.z, xv.w), s1[i] = racc<OP>(xv.y, s2[i]), s0[i] = racc<OP>(xv.x, s1[i]);
+                    vu[i] = vd[i] = racc<OP>(p3[i], xv.w);
+                    E[i] = F[i] = id;
+                }
+                // exclusive prefix E / suffix F of the lane totals inside each block of G lanes (Kogge-Stone; the
+                // inclusive values vu / vd only feed the next step)
+#pragma unroll
+                for (int k = 0; k < STEPS; k++) {
+                    float ou[IL], od[IL];
+#pragma unroll
+                    for (int i = 0; i < IL; i++) {
+                        ou[i] = __shfl_up_sync(0xffffffffu, vu[i], 1 << k, G);
+                        od[i] = __shfl_down_sync(0xffffffffu, vd[i], 1 << k, G);
+                    }
+#pragma unroll
+                    for (int i = 0; i < IL; i++) {
+                        if (pu[k]) vu[i] = racc<OP>(ou[i], vu[i]), E[i] = racc<OP>(ou[i], E[i]);
+                        if (pd[k]) vd[i] = racc<OP>(vd[i], od[i]), F[i] = racc<OP>(F[i], od[i]);
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < IL; i++) {
-                    if (pu[k]) vu[i] = racc<OP>(ou[i], vu[i]), E[i] = racc<OP>(ou[i], E[i]);
-                    if (pd[k]) vd[i] = racc<OP>(vd[i], od[i]), F[i] = racc<OP>(F[i], od[i]);
+                    const float4 xv = cur[i];
+                    const float nx0 = E[i], nx1 = racc<OP>(E[i], xv.x), nx2 = racc<OP>(E[i], p2[i]), nx3 = racc<OP>(E[i], p3[i]);
+                    if (g + i > 0 || batch > 0) {  // emit the previous row: its own suffixes (+) the next block's exclusive prefixes
+                        float4 o;
+                        if constexpr (G == 32) {
+                            o.x = nx0, o.y = nx1, o.z = nx2, o.w = nx3;
+                        } else {
+                            o.x = __shfl_sync(0xffffffffu, low ? nx0 : cx0, partner);
+                            o.y = __shfl_sync(0xffffffffu, low ? nx1 : cx1, partner);
+                            o.z = __shfl_sync(0xffffffffu, low ? nx2 : cx2, partner);
+                            o.w = __shfl_sync(0xffffffffu, low ? nx3 : cx3, partner);
+                        }
+                        o.x = racc<OP>(cs0, o.x), o.y = racc<OP>(cs1, o.y), o.z = racc<OP>(cs2, o.z), o.w = racc<OP>(cs3, o.w);
+                        if (!ident) {  // with the identity as init the fold changes nothing: no sum here is -0, no max/min is NaN
+                            o.x = rfinal<OP>(init, o.x), o.y = rfinal<OP>(init, o.y), o.z = rfinal<OP>(init, o.z), o.w = rfinal<OP>(init, o.w);
+                        }
+                        float* const d = drow + (g + i) * 128;
+                        if constexpr (INTERIOR) {
+                            __stcs(reinterpret_cast<float4*>(d), o);
+                        } else {
+                            const uint32_t el = (r0 + g + i - 1) * 128 + 4 * lane;  // this lane's first output of the emitted row
+                            if (el + 4 <= nout) {
+                                __stcs(reinterpret_cast<float4*>(d), o);
+                            } else {
+                                if (el + 0 < nout) __stcs(d + 0, o.x);
+                                if (el + 1 < nout) __stcs(d + 1, o.y);
+                                if (el + 2 < nout) __stcs(d + 2, o.z);
+                            }
+                        }
+                    }
+                    cs0 = racc<OP>(s0[i], F[i]), cs1 = racc<OP>(s1[i], F[i]), cs2 = racc<OP>(s2[i], F[i]), cs3 = racc<OP>(xv.w, F[i]);
+                    cx0 = nx0, cx1 = nx1, cx2 = nx2, cx3 = nx3;
                 }
             }
-#pragma unroll
-            for (int i = 0; i < IL; i++) {
-                const float4 xv = cur[g + i];
-                const float nx0 = E[i], nx1 = racc<OP>(E[i], xv.x), nx2 = racc<OP>(E[i], p2[i]), nx3 = racc<OP>(E[i], p3[i]);
-                if (g + i > 0 || batch > 0) {  // emit the previous row: its own suffixes (+) the next block's exclusive prefixes
-                    float4 o;
-                    if constexpr (G == 32) {
-                        o.x = nx0, o.y = nx1, o.z = nx2, o.w = nx3;
-                    } else {
-                        o.x = __shfl_sync(0xffffffffu, low ? nx0 : cx0, partner);
-                        o.y = __shfl_sync(0xffffffffu, low ? nx1 : cx1, partner);
-                        o.z = __shfl_sync(0xffffffffu, low ? nx2 : cx2, partner);
-                        o.w = __shfl_sync(0xffffffffu, low ? nx3 : cx3, partner);
-                    }
-                    o.x = racc<OP>(cs0, o.x), o.y = racc<OP>(cs1, o.y), o.z = racc<OP>(cs2, o.z), o.w = racc<OP>(cs3, o.w);
-                    if (!ident) {  // with the identity as init the fold changes nothing: no sum here is -0, no max/min is NaN
-                        o.x = rfinal<OP>(init, o.x), o.y = rfinal<OP>(init, o.y), o.z = rfinal<OP>(init, o.z), o.w = rfinal<OP>(init, o.w);
-                    }
-                    const uint32_t e = (r0 + g + i - 1) * 128;  // first output of the row being emitted
-                    if (all_full || e + 128 <= nout) {
-                        __stcs(reinterpret_cast<float4*>(dst + e), o);
-                    } else {
-                        const uint32_t el = e + 4 * lane;
-                        if (el + 0 < nout) __stcs(dst + e + 0, o.x);
-                        if (el + 1 < nout) __stcs(dst + e + 1, o.y);
-                        if (el + 2 < nout) __stcs(dst + e + 2, o.z);
-                        if (el + 3 < nout) __stcs(dst + e + 3, o.w);
-                    }
-                }
-                cs0 = racc<OP>(s0[i], F[i]), cs1 = racc<OP>(s1[i], F[i]), cs2 = racc<OP>(s2[i], F[i]), cs3 = racc<OP>(xv.w, F[i]);
-                cx0 = nx0, cx1 = nx1, cx2 = nx2, cx3 = nx3;
-            }
-        }
+        };
+        if (interior) body(std::true_type{});
+        else body(std::false_type{});
     }
+    cp_async_wait<0>();
+}
+
+template <int OP, int W, int B, int S, int NB, int WPC>
+static bool launch_window_shfl_cfg(const float* src, float* out, uint32_t nout, uint32_t rows, long long row_stride, float init, long per_sm) {
+    const float ident_tab[AL_REDOP_COUNT] = {0.0f, -INFINITY, INFINITY, 1.0f};
+    const int init_is_identity = memcmp(&init, &ident_tab[OP], sizeof(float)) == 0;
+    constexpr size_t smem = (size_t)WPC * S * B * 512;
+    constexpr int R = B * NB - 1;
+    const uint64_t rows128 = ((uint64_t)nout + 127) / 128;
+    const uint64_t segs_per_row = (rows128 + R - 1) / R;
+    const uint64_t all_segs = segs_per_row * rows;
+    if (all_segs >= (1ull << 31)) return set_error("NotImplementedError: too many window segments"), false;
+    static bool configured = false;
+    if (!configured) {
+        if (!cuda_ok(cudaFuncSetAttribute(reduce_window_shfl_kernel<OP, W, B, S, NB, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute"))
+            return false;
+        configured = true;
+    }
+    uint64_t blocks = (all_segs + WPC - 1) / WPC;
+    if (blocks > (uint64_t)kNumSMs * per_sm) blocks = (uint64_t)kNumSMs * per_sm;
+    reduce_window_shfl_kernel<OP, W, B, S, NB, WPC><<<(unsigned)blocks, WPC * 32, smem, rt().stream>>>(src, out, nout, (uint32_t)all_segs, (uint32_t)segs_per_row, row_stride, init, init_is_identity);
+    note_launch("reduce_window_shfl");
+    return check_launch("reduce_window_shfl");
 }
 
 template <int OP, int W>
 static bool launch_window_shfl(const float* src, float* out, uint32_t nout, uint32_t rows, long long row_stride, float init) {
-    const float ident_tab[AL_REDOP_COUNT] = {0.0f, -INFINITY, INFINITY, 1.0f};
-    const int init_is_identity = memcmp(&init, &ident_tab[OP], sizeof(float)) == 0;
-    const long variant = rt().window_shfl;  // 1: 8 rows x 4 batches per segment, 2: 4 rows x 8 batches
-    const uint64_t rows128 = ((uint64_t)nout + 127) / 128;
-    const uint64_t segs_per_row = (rows128 + 30) / 31;  // both variants: R = 31
-    const uint64_t all_segs = segs_per_row * rows;
-    if (all_segs >= (1ull << 31)) return set_error("NotImplementedError: too many window segments"), false;
-    const long per_sm = rt().window_ctas_per_sm > 0 ? rt().window_ctas_per_sm : 4;
-    uint64_t blocks = (all_segs + 3) / 4;
-    if (blocks > (uint64_t)kNumSMs * per_sm) blocks = (uint64_t)kNumSMs * per_sm;
-    if (variant == 2)
-        reduce_window_shfl_kernel<OP, W, 4, 8><<<(unsigned)blocks, kShflThreads, 0, rt().stream>>>(src, out, nout, (uint32_t)all_segs, (uint32_t)segs_per_row, row_stride, init, init_is_identity);
-    else
-        reduce_window_shfl_kernel<OP, W, 8, 4><<<(unsigned)blocks, kShflThreads, 0, rt().stream>>>(src, out, nout, (uint32_t)all_segs, (uint32_t)segs_per_row, row_stride, init, init_is_identity);
-    note_launch("reduce_window_shfl");
-    return check_launch("reduce_window_shfl");
+    // Ring shape (rows per batch, stages, batches per segment, warps per CTA) and CTAs per SM. Measured on C5a inside a
+    // busy stretch (power cap active, tools/microbench.py c5a_attrib): 16 x 2 x 1 with 6 resident warps per SM and
+    // 12 x 2 x 1 with 8 both run at 0.335 ms (6.4 TB/s); more resident warps are SLOWER (10-12 warps: 0.36-0.40 ms).
+    const long v = rt().window_shfl;
+    const long per_sm = rt().window_ctas_per_sm > 0 ? rt().window_ctas_per_sm : (v == 1 ? 3 : 2);
+    switch (v) {
+        case 2: return launch_window_shfl_cfg<OP, W, 12, 2, 1, 4>(src, out, nout, rows, row_stride, init, per_sm);
+        case 3: return launch_window_shfl_cfg<OP, W, 16, 2, 2, 4>(src, out, nout, rows, row_stride, init, per_sm);
+        default: return launch_window_shfl_cfg<OP, W, 16, 2, 1, 2>(src, out, nout, rows, row_stride, init, per_sm);
+    }
 }
 
 template <int OP, int W>

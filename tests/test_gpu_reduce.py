@@ -174,7 +174,8 @@ def test_window_kernel_variants_agree(al, orc, rng, w):
     vn = np.lib.stride_tricks.as_strided(base, shape=(n - w + 1, w), strides=(4, 4))
     for op in ("sum", "max", "min"):
         want = orc.reduce(op, vn, (1,))
-        for shfl, whole, name in ((1, 0, b"reduce_window_shfl"), (2, 0, b"reduce_window_shfl"), (0, 0, b"reduce_window"), (0, 1, b"reduce_window")):
+        for shfl, whole, name in ((1, 0, b"reduce_window_shfl"), (2, 0, b"reduce_window_shfl"), (3, 0, b"reduce_window_shfl"),
+                                  (0, 0, b"reduce_window"), (0, 1, b"reduce_window")):
             lib.al_set_tuning(b"window_shfl", shfl)
             lib.al_set_tuning(b"window_whole_blocks", whole)
             try:
@@ -188,7 +189,7 @@ def test_window_kernel_variants_agree(al, orc, rng, w):
 
 
 @pytest.mark.parametrize("w", [8, 16, 32, 64, 128])
-@pytest.mark.parametrize("nout", [4, 124, 128, 132, 31 * 128 - 4, 31 * 128, 31 * 128 + 4, 62 * 128 + 8, 1000003])
+@pytest.mark.parametrize("nout", [4, 124, 128, 132, 15 * 128 - 4, 15 * 128, 15 * 128 + 4, 30 * 128 + 8, 2 * 3 * 148 * 15 * 128 + 128 + 3, 1000003])
 def test_shuffle_window_kernel_edges(al, orc, rng, w, nout):
     """Segment / row / vector boundaries of the register/shuffle kernel: outputs per signal just below, at and just above
     a 128-output row and a 31-row segment, odd lengths (scalar tail stores, partial last vector of the source), a

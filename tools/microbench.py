@@ -109,10 +109,10 @@ def bench_window():
     n, w = 1 << 28, 64
     base = rnd((n,), 1)
     win = lambda ww: base.as_strided(shape=(n - ww + 1, ww), stride=(1, 1))  # noqa: E731
-    for variant in (1, 2):
-        for per_sm in (0, 3, 4, 5, 6, 8):
+    for variant, per_sms in ((1, (2, 3, 4)), (2, (2, 3)), (3, (2,))):
+        for per_sm in per_sms:
             tune(window_shfl=variant, window_ctas_per_sm=per_sm)
-            timed(lambda: win(w).reduce_sum(dims=[1]), 4 * n + 4 * (n - w + 1), f"window-64 reduce_sum 2^28 shfl variant={variant} ctas/SM={per_sm or 'default'}")
+            timed(lambda: win(w).reduce_sum(dims=[1]), 4 * n + 4 * (n - w + 1), f"window-64 reduce_sum 2^28 shfl ring variant={variant} ctas/SM={per_sm}", reps=5)
     tune(window_shfl=0, window_ctas_per_sm=0)
     timed(lambda: win(w).reduce_sum(dims=[1]), 4 * n + 4 * (n - w + 1), "window-64 reduce_sum 2^28 shared-memory half-block kernel")
     tune(window_shfl=1)
@@ -172,36 +172,33 @@ def bench_c5a_attrib():
             del r
         print(f"{label:64s} median {statistics.median(ts):.4f} ms = {nbytes / statistics.median(ts) / 1e6:7.1f} GB/s  all {[round(t, 4) for t in ts]}  [{lib.al_last_kernel().decode()}] smi: {smi_clock()}", flush=True)
 
-    for variant in (1, 0):
-        tune(window_shfl=variant)
-        print(f"--- window_shfl={variant}", flush=True)
+    for variant, per_sm in ((0, 0), (1, 3), (2, 2), (3, 2)):
+        tune(window_shfl=variant, window_ctas_per_sm=per_sm)
+        print(f"--- window_shfl={variant} ctas/SM={per_sm}", flush=True)
         for _ in range(3):
             r = c5a()
             del r
         al.synchronize()
-        time.sleep(2.0)
-        one("after a 2 s idle gap (first = cold clocks)")
-        one("back to back")
-        one("after reduce_sum(X, dims=(3,)) [read-heavy 4 GiB]", lambda: X.reduce_sum(dims=(3,)))
+        time.sleep(1.0)
+        one("after a 1 s idle gap")
         one("after reduce_sum(X, dims=(0,)) [64 MiB output left dirty in L2]", lambda: X.reduce_sum(dims=(0,)))
-        one("after a+b [1 GiB written]", lambda: a + b)
         th = threading.Thread(target=sampler, daemon=True)
         th.start()
-        t_end = time.perf_counter() + 4.0
-        while time.perf_counter() < t_end:   # long busy stretch: the power cap, if any, sets in here
+        t_end = time.perf_counter() + 2.5
+        while time.perf_counter() < t_end:   # long busy stretch: the power cap sets in here
             for _ in range(20):
                 r = a + b
                 del r
                 r = X.reduce_sum(dims=(0,))
                 del r
             al.synchronize()
-        one("inside a 4 s busy stretch (after reduce dims=(0,))", lambda: X.reduce_sum(dims=(0,)), reps=9)
+        one("inside a busy stretch (after reduce dims=(0,))", lambda: X.reduce_sum(dims=(0,)), reps=9)
         stop.set()
         th.join()
         stop.clear()
-        print("   smi during the busy stretch (sm MHz, W, sw_power_cap):", [s for _, s in samples[:: max(len(samples) // 12, 1)]], flush=True)
+        print("   smi during the busy stretch (sm MHz, W, sw_power_cap):", [s for _, s in samples[:: max(len(samples) // 6, 1)]], flush=True)
         samples.clear()
-    tune(window_shfl=1)
+    tune(window_shfl=1, window_ctas_per_sm=0)
 
 
 def bench_reduce():
