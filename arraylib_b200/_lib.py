@@ -55,6 +55,7 @@ def _load():
 
     sig("al_init", C.c_int, C.c_int)
     sig("al_device", C.c_int)
+    sig("al_device_count", C.c_int)
     sig("al_sync", C.c_int)
     sig("al_stream", C.c_void_p)
     sig("al_last_error", C.c_char_p)

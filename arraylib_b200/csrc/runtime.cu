@@ -310,6 +310,15 @@ int al_init(int device) {
 
 int al_device(void) { return g_rt.device; }
 
+int al_device_count(void) {  // CUDA devices visible to this process (0 when there is no usable driver)
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return count;
+}
+
 // Blocks that an in-flight asynchronous download still reads: they hold one extra reference until
 // the copy stream has been drained, so the allocator cannot hand them to a new owner early.
 static std::vector<NDArray*> g_pending_downloads;

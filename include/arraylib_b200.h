@@ -72,6 +72,7 @@ enum al_redop { AL_RSUM = 0, AL_RMAX, AL_RMIN, AL_RPROD, AL_REDOP_COUNT };
 /* ---- runtime (new; the reference has no device, stream or error channel) ------------------ */
 int al_init(int device);             /* bind the process to one GPU; idempotent. <0 = use ARRAYLIB_DEVICE / LOCAL_RANK / 0 */
 int al_device(void);                 /* bound device ordinal, -1 before al_init */
+int al_device_count(void);            /* CUDA devices visible to this process */
 int al_sync(void);                   /* block until the library stream is idle */
 void* al_stream(void);               /* the cudaStream_t all work is enqueued on */
 const char* al_last_error(void);     /* thread-local; "" when the last call succeeded */
