@@ -68,6 +68,7 @@ def _load():
     sig("al_event_elapsed", C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float))
     sig("al_bytes_in_use", C.c_uint64)
     sig("al_trim_pool", C.c_int)
+    sig("al_bytes_cached", C.c_uint64)
     sig("al_host_alloc", C.c_void_p, C.c_size_t)
     sig("al_host_free", C.c_int, C.c_void_p)
     sig("al_set_tuning", C.c_int, C.c_char_p, C.c_long)

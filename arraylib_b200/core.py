@@ -356,21 +356,26 @@ del _op
 def apply(fn, array) -> NDArray:
     """Elementwise map on the device. `fn` is resolved, in this order, to
       1. a named device ufunc by identity / name (math.sqrt, np.log, abs, ...);
-      2. a traced FP64 tape: arithmetic lambdas such as `lambda x: 2 * x * x + 1`, `lambda x: (x + 1) / (x - 1)`
-         or `lambda x: np.exp(-x * x)` are recorded on a scalar proxy and run as one kernel in double
-         precision with one final rounding (the arithmetic of the reference's per-element Python callback);
-      3. a named device ufunc by probe fingerprint (e.g. `lambda x: math.sqrt(x)`).
-    Anything else raises NotImplementedError -- there is no CPU fallback."""
+      2. a traced FP64 tape: arithmetic lambdas such as `lambda x: 2 * x * x + 1`, `lambda x: (x + 1) / (x - 1)`,
+         `lambda x: np.exp(-x * x)` or `lambda x: math.sqrt(x) + 1` are recorded on a scalar proxy and run as one
+         kernel in double precision with one final rounding (the arithmetic of the reference's per-element
+         Python callback); a trace of exactly one ufunc (`lambda x: math.sqrt(x)`) runs the named kernel.
+    Anything else (data-dependent branches, builtin max/min on the value, float(x)) raises NotImplementedError --
+    there is no CPU fallback and no guessing from sample values."""
     assert callable(fn) or isinstance(fn, str)
     assert isinstance(array, NDArray)
     code = _uf.resolve_by_name(fn)
     if code is None and not isinstance(fn, str):
-        from .lazy import trace_unary  # (the package also exports a FUNCTION named `lazy`)
-        traced = trace_unary(fn, array)
-        if traced is not None:
-            return traced
+        from .lazy import single_instruction, trace_unary  # (the package also exports a FUNCTION named `lazy`)
+        one = single_instruction(fn, 1)
+        if one is not None and one[0] == 1:
+            code = UFUNCS.index(one[1])
+        else:
+            traced = trace_unary(fn, array)
+            if traced is not None:
+                return traced
     if code is None:
-        code = _uf.resolve_unary(fn)
+        code = _uf.resolve_unary(fn)  # raises with the explanation
     return _new(lib.array_op_named(code, array.buffer))
 
 

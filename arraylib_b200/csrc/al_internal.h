@@ -84,9 +84,12 @@ size_t count_of(const size_t* shape, size_t ndim);  // zero extents count as 1 (
 NDArray* new_array(const size_t* shape, size_t ndim);  // contiguous, fresh device buffer
 NDArray* new_view(const NDArray* src, const size_t* shape, const size_t* stride, size_t ndim,
                   size_t extra_offset);
+void release_array(NDArray* a);  // array_free without touching the thread's error slot (internal clean-up)
 bool is_contiguous(const NDArray* a);
 size_t view_offset(const NDArray* a);  // ptr - mem, in elements
 bool valid(const NDArray* a, const char* who);
+bool valid_mut(const NDArray* a, const char* who);  // valid() for an array about to be WRITTEN in place: also orders the write after pending async downloads of its buffer
+void await_downloads(const Data* d);
 
 // ---- folded layouts --------------------------------------------------------------------------
 // Dimensions are stored INNERMOST FIRST (index 0 = fastest-varying logical axis).

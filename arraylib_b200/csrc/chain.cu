@@ -612,7 +612,7 @@ extern "C" NDArray* array_chain_eval(const NDArray* const* inputs, size_t n_inpu
     }
     if (!ok) {
         std::string keep = last_error_string();
-        array_free(out);
+        release_array(out);
         restore_error(keep);
         return nullptr;
     }
@@ -683,7 +683,7 @@ extern "C" NDArray* array_tape_eval_f64(const NDArray* const* inputs, size_t n_i
     }
     if (!ok) {
         std::string keep = last_error_string();
-        array_free(out);
+        release_array(out);
         restore_error(keep);
         return nullptr;
     }

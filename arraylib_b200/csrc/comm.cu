@@ -437,7 +437,7 @@ int al_comm_init(const char id_bytes[128], int rank, int world) {
 
 int al_comm_allreduce(NDArray* a, int redop) {
     AL_ENTER;
-    if (!valid(a, "al_comm_allreduce")) return -1;
+    if (!valid_mut(a, "al_comm_allreduce")) return -1;
     if (!g_nccl.comm) return set_error("RuntimeError: al_comm_init has not been called"), -1;
     if (!is_contiguous(a)) return set_error("ValueError: allreduce needs a contiguous array"), -1;
     const ncclRedOp_t ops[AL_REDOP_COUNT] = {ncclSum, ncclMax, ncclMin, ncclProd};
@@ -458,7 +458,7 @@ int al_comm_allreduce(NDArray* a, int redop) {
 
 int al_comm_allgather(const NDArray* shard, NDArray* full) {
     AL_ENTER;
-    if (!valid(shard, "al_comm_allgather") || !valid(full, "al_comm_allgather")) return -1;
+    if (!valid(shard, "al_comm_allgather") || !valid_mut(full, "al_comm_allgather")) return -1;
     if (!g_nccl.comm) return set_error("RuntimeError: al_comm_init has not been called"), -1;
     if (!is_contiguous(shard) || !is_contiguous(full)) return set_error("ValueError: allgather needs contiguous arrays"), -1;
     size_t n = count_of(shard->lay->shape, shard->lay->ndim);
@@ -471,7 +471,7 @@ int al_comm_allgather(const NDArray* shard, NDArray* full) {
 
 int al_comm_alltoall(const NDArray* send, NDArray* recv) {
     AL_ENTER;
-    if (!valid(send, "al_comm_alltoall") || !valid(recv, "al_comm_alltoall")) return -1;
+    if (!valid(send, "al_comm_alltoall") || !valid_mut(recv, "al_comm_alltoall")) return -1;
     if (!g_nccl.comm) return set_error("RuntimeError: al_comm_init has not been called"), -1;
     if (!is_contiguous(send) || !is_contiguous(recv)) return set_error("ValueError: alltoall needs contiguous arrays"), -1;
     const size_t n = count_of(send->lay->shape, send->lay->ndim);
@@ -544,7 +544,7 @@ static NDArray* comm_reduce(int redop, const NDArray* shard, const size_t* dims,
             if (!part) return nullptr;
             bool ok = peer_push(part->ptr, nout, map);
             std::string keep = last_error_string();
-            array_free(part);
+            release_array(part);
             restore_error(keep);
             if (!ok) return nullptr;
         }
@@ -552,7 +552,7 @@ static NDArray* comm_reduce(int redop, const NDArray* shard, const size_t* dims,
         if (!out) return nullptr;
         if (!peer_finish(redop, out->ptr, nout, ident[redop], scatter)) {
             std::string keep = last_error_string();
-            array_free(out);
+            release_array(out);
             restore_error(keep);
             return nullptr;
         }
@@ -566,8 +566,8 @@ static NDArray* comm_reduce(int redop, const NDArray* shard, const size_t* dims,
         NDArray* out = new_array(lshape, nd);
         bool ok = out && nccl_ok(g_nccl.ReduceScatter(part->ptr, out->ptr, nout / g_nccl.world, ncclFloat32, ops[redop], g_nccl.comm, rt().stream), "ncclReduceScatter");
         std::string keep = last_error_string();
-        array_free(part);
-        if (!ok && out) array_free(out);
+        release_array(part);
+        if (!ok && out) release_array(out);
         restore_error(keep);
         if (!ok) return nullptr;
         note_launch("nccl_reduce_scatter");
@@ -575,7 +575,7 @@ static NDArray* comm_reduce(int redop, const NDArray* shard, const size_t* dims,
     }
     if (!nccl_ok(g_nccl.AllReduce(part->ptr, part->ptr, nout, ncclFloat32, ops[redop], g_nccl.comm, rt().stream), "ncclAllReduce")) {
         std::string keep = last_error_string();
-        array_free(part);
+        release_array(part);
         restore_error(keep);
         return nullptr;
     }

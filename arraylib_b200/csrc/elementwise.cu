@@ -90,7 +90,7 @@ static NDArray* run_to_new(EwCall call, size_t ndim, const size_t* shape, const 
     call.out = out->ptr;
     if (!fold_layout(ndim, shape, out->lay->stride, call.nin, strides, &fo) || !launch_elementwise(call, fo)) {
         std::string keep = last_error_string();
-        array_free(out);
+        release_array(out);
         restore_error(keep);
         return nullptr;
     }
@@ -283,7 +283,7 @@ static bool slice_layout(const NDArray* dst, const size_t* start, const size_t* 
 NDArray* array_set_view_from_scalar(NDArray* dst, f32 value, const size_t* start, const size_t* end,
                                     const size_t* step) {
     AL_ENTER;
-    if (!valid(dst, "array_set_view_from_scalar")) return nullptr;
+    if (!valid_mut(dst, "array_set_view_from_scalar")) return nullptr;
     size_t nd = dst->lay->ndim, shape[64], stride[64], off;
     AL_REQUIRE(nd <= 64, "ValueError: too many dimensions");
     if (!slice_layout(dst, start, end, step, shape, stride, &off)) return nullptr;
@@ -296,7 +296,7 @@ NDArray* array_set_view_from_scalar(NDArray* dst, f32 value, const size_t* start
 NDArray* array_set_view_from_array(NDArray* dst, const NDArray* src, const size_t* start, const size_t* end,
                                    const size_t* step) {
     AL_ENTER;
-    if (!valid(dst, "array_set_view_from_array") || !valid(src, "array_set_view_from_array")) return nullptr;
+    if (!valid_mut(dst, "array_set_view_from_array") || !valid(src, "array_set_view_from_array")) return nullptr;
     size_t nd = dst->lay->ndim, shape[64], stride[64], off;
     AL_REQUIRE(nd <= 64, "ValueError: too many dimensions");
     AL_REQUIRE(src->lay->ndim == nd, "ValueError: dimension mismatch.");

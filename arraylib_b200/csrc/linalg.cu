@@ -37,7 +37,7 @@ NDArray* array_array_matmul(const NDArray* lhs, const NDArray* rhs) {
                                                  (uint32_t)K, (uint32_t)N);
     note_launch("matmul_compat");
     if (!check_launch("matmul")) {
-        array_free(out);
+        release_array(out);
         return nullptr;
     }
     return out;
@@ -56,7 +56,7 @@ NDArray* array_array_dot(const NDArray* lhs, const NDArray* rhs) {
     size_t dims[1] = {0};
     NDArray* out = array_reduce_sum(prod, dims, 1);
     std::string keep = last_error_string();
-    array_free(prod);
+    release_array(prod);
     restore_error(keep);
     return out;
 }

@@ -1489,7 +1489,7 @@ NDArray* reduce_impl(int redop, const NDArray* src, const size_t* dims, size_t n
         }
         std::string keep = last_error_string();
         for (NDArray* t : {lo, hi, rlo, rhi})
-            if (t) array_free(t);
+            if (t) release_array(t);
         restore_error(keep);
         return both;
     }
@@ -1508,7 +1508,7 @@ NDArray* reduce_impl(int redop, const NDArray* src, const size_t* dims, size_t n
     }
     if (!ok) {
         std::string keep = last_error_string();
-        array_free(out);
+        release_array(out);
         restore_error(keep);
         return nullptr;
     }

@@ -77,6 +77,61 @@ static void await_upload(const Data* d) {
     g_uploads.erase(it);
 }
 
+static void free_layout(Layout* lay);
+
+// arraylib.c:223-231 without the entry-point prologue: internal callers (error paths, temporaries, the download
+// reaper) release arrays through this so that the thread's error message survives the clean-up.
+void release_array(NDArray* a) {
+    if (!a) return;
+    if (a->data && __atomic_sub_fetch(&a->data->refs, 1, __ATOMIC_ACQ_REL) == 0) {
+        await_upload(a->data);  // never used: the block must still not be recycled before its upload has landed
+        g_rt.bytes_in_use -= a->data->size * sizeof(float);
+        device_free(a->data->mem);
+        free(a->data);
+    }
+    free_layout(a->lay);
+    free(a);
+}
+
+// Blocks that an in-flight asynchronous download still reads: they hold one extra reference until their copy has
+// completed (an event recorded behind it on the D2H stream), so the allocator cannot hand them to a new owner
+// early. Finished entries are reaped whenever a new download is queued, whenever the allocator has to go to the
+// driver, and in al_sync() -- a pipeline that never calls al_sync() holds at most the downloads in flight.
+struct PendingDownload {
+    NDArray* hold;
+    cudaEvent_t done;
+};
+static std::vector<PendingDownload> g_pending_downloads;
+
+static void reap_downloads(bool wait_for_all) {
+    if (g_pending_downloads.empty()) return;
+    size_t kept = 0;
+    for (size_t i = 0; i < g_pending_downloads.size(); i++) {
+        PendingDownload& p = g_pending_downloads[i];
+        bool finished = wait_for_all;
+        if (!finished) {
+            cudaError_t e = cudaEventQuery(p.done);
+            if (e != cudaSuccess) cudaGetLastError();  // cudaErrorNotReady is not sticky, but keep the slot clean
+            finished = (e == cudaSuccess);
+        }
+        if (finished) {
+            release_array(p.hold);
+            g_event_pool.push_back(p.done);
+        } else {
+            g_pending_downloads[kept++] = p;
+        }
+    }
+    g_pending_downloads.resize(kept);
+}
+
+// In-place writers (setters, array_write_base, in-place collectives) run on the compute stream; an asynchronous
+// download of the same buffer runs on the D2H stream and is only ordered AFTER earlier compute work. Make the
+// compute stream wait for the pending downloads of `d` so that the host never sees a mix of old and new values.
+void await_downloads(const Data* d) {
+    for (const PendingDownload& p : g_pending_downloads)
+        if (p.hold->data == d) cudaStreamWaitEvent(g_rt.stream, p.done, 0);
+}
+
 bool valid(const NDArray* a, const char* who) {
     if (a && a->data && a->lay && a->lay->ndim > 0 && a->ptr) {
         await_upload(a->data);
@@ -84,6 +139,12 @@ bool valid(const NDArray* a, const char* who) {
     }
     set_error("TypeError: %s got a NULL or malformed array", who);
     return false;
+}
+
+bool valid_mut(const NDArray* a, const char* who) {
+    if (!valid(a, who)) return false;
+    await_downloads(a->data);
+    return true;
 }
 
 size_t view_offset(const NDArray* a) { return (size_t)(a->ptr - a->data->mem); }
@@ -125,10 +186,48 @@ static void release_cached_blocks() {
     g_cached_bytes = 0;
 }
 
+// The cache may hold at most `cache_limit` bytes of idle blocks (default: half of the device's memory, so a
+// workload whose sizes drift cannot strand the whole HBM in blocks nobody asks for again; `cache_limit_mb`
+// tuning knob). Over the limit the LARGEST idle blocks go back to the driver first: they are the ones another
+// size class cannot reuse. cudaFree waits for the device, which is what makes the early release safe.
+static size_t g_cache_limit = 0;
+
+static void trim_cache_to_limit() {
+    if (g_cache_limit == 0) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        g_cache_limit = total_b / 2;
+    }
+    while (g_cached_bytes > g_cache_limit && !g_free_blocks.empty()) {
+        auto last = std::prev(g_free_blocks.end());
+        cudaFree(last->second);
+        g_block_size.erase(last->second);
+        g_cached_bytes -= last->first;
+        g_free_blocks.erase(last);
+    }
+}
+
+void set_cache_limit(size_t bytes) {
+    g_cache_limit = bytes;  // 0 = back to the default (half of the device's memory)
+    trim_cache_to_limit();
+}
+size_t cached_bytes() { return g_cached_bytes; }
+
 void* device_alloc(size_t bytes) {
     const size_t want = round_block(bytes ? bytes : 1);
     auto it = g_free_blocks.lower_bound(want);
     if (it != g_free_blocks.end() && it->first <= want + want / 8) {  // at most 12.5% slack
+        void* p = it->second;
+        g_cached_bytes -= it->first;
+        g_free_blocks.erase(it);
+        return p;
+    }
+    reap_downloads(false);  // finished downloads hand their blocks back to the cache first
+    it = g_free_blocks.lower_bound(want);
+    if (it != g_free_blocks.end() && it->first <= want + want / 8) {
         void* p = it->second;
         g_cached_bytes -= it->first;
         g_free_blocks.erase(it);
@@ -156,6 +255,7 @@ void device_free(void* p) {
     if (it == g_block_size.end()) return;
     g_free_blocks.emplace(it->second, p);
     g_cached_bytes += it->second;
+    trim_cache_to_limit();
 }
 
 static Layout* make_layout(const size_t* shape, const size_t* stride, size_t ndim) {
@@ -319,23 +419,13 @@ int al_device_count(void) {  // CUDA devices visible to this process (0 when the
     return count;
 }
 
-// Blocks that an in-flight asynchronous download still reads: they hold one extra reference until
-// the copy stream has been drained, so the allocator cannot hand them to a new owner early.
-static std::vector<NDArray*> g_pending_downloads;
-
-static void drain_pending_downloads() {
-    std::vector<NDArray*> done;
-    done.swap(g_pending_downloads);
-    for (NDArray* a : done) array_free(a);
-}
-
 int al_sync(void) {
     AL_ENTER;
     if (g_rt.device < 0) return 0;
     bool ok = cuda_ok(cudaStreamSynchronize(g_rt.h2d_stream), "cudaStreamSynchronize(h2d)") &&
               cuda_ok(cudaStreamSynchronize(g_rt.stream), "cudaStreamSynchronize") &&
               cuda_ok(cudaStreamSynchronize(g_rt.d2h_stream), "cudaStreamSynchronize(d2h)");
-    drain_pending_downloads();
+    reap_downloads(true);  // the D2H stream is idle (or broken): nothing reads the held blocks any more
     for (auto& kv : g_uploads) g_event_pool.push_back(kv.second);  // the H2D stream is idle: nothing left to wait for
     g_uploads.clear();
     if (ok && comm_error_pending()) ok = false;  // a peer-memory collective gave up waiting for another rank
@@ -348,6 +438,7 @@ const char* al_version(void) { return "arraylib_b200 0.1 (sm_100a)"; }
 uint64_t al_launch_count(void) { return g_rt.launches; }
 const char* al_last_kernel(void) { return g_rt.last_kernel; }
 uint64_t al_bytes_in_use(void) { return g_rt.bytes_in_use; }
+uint64_t al_bytes_cached(void) { return cached_bytes(); }
 
 int al_timer_start(void) {
     AL_ENTER;
@@ -413,6 +504,7 @@ int al_set_tuning(const char* key, long value) {
     if (k == "stream_store_min_bytes") g_rt.stream_store_min_bytes = value;
     else if (k == "ew_unroll") (void)value;  // swept once (profiles/r1_micro_stream_variants.log), now fixed at 4
     else if (k == "load_policy") g_rt.load_policy = value;
+    else if (k == "cache_limit_mb") set_cache_limit((size_t)(value < 0 ? 0 : value) << 20);
     else if (k == "force_general") g_rt.force_general = value;
     else if (k == "reduce_splits") g_rt.reduce_splits = value;
     else if (k == "reduce_sequential") g_rt.reduce_sequential = value;
@@ -530,14 +622,7 @@ void array_free(NDArray* a) {
         set_error("TypeError: array_free on NULL");
         return;
     }
-    if (a->data && __atomic_sub_fetch(&a->data->refs, 1, __ATOMIC_ACQ_REL) == 0) {
-        await_upload(a->data);  // never used: the block must still not be recycled before its upload has landed
-        g_rt.bytes_in_use -= a->data->size * sizeof(float);
-        device_free(a->data->mem);
-        free(a->data);
-    }
-    free_layout(a->lay);
-    free(a);
+    release_array(a);
 }
 
 NDArray* array_shallow_copy(const NDArray* src) {
@@ -613,6 +698,7 @@ int array_to_host_async(const NDArray* src, f32* dst) {
     AL_ENTER;
     if (!valid(src, "array_to_host_async")) return -1;
     if (!dst) return set_error("TypeError: array_to_host_async got a NULL destination"), -1;
+    reap_downloads(false);
     size_t n = count_of(src->lay->shape, src->lay->ndim);
     NDArray* hold = is_contiguous(src) ? array_shallow_copy(src) : array_deep_copy(src);
     if (!hold) return -1;
@@ -620,7 +706,16 @@ int array_to_host_async(const NDArray* src, f32* dst) {
               cuda_ok(cudaStreamWaitEvent(g_rt.d2h_stream, g_rt.ev_copy, 0), "cudaStreamWaitEvent") &&
               cuda_ok(cudaMemcpyAsync(dst, hold->ptr, n * sizeof(float), cudaMemcpyDeviceToHost, g_rt.d2h_stream),
                       "cudaMemcpyAsync(D2H)");
-    g_pending_downloads.push_back(hold);  // released by al_sync()
+    cudaEvent_t done = take_event();
+    if (ok) ok = done && cuda_ok(cudaEventRecord(done, g_rt.d2h_stream), "cudaEventRecord");
+    if (ok) {
+        g_pending_downloads.push_back({hold, done});  // released once `done` has fired (reap_downloads)
+    } else {  // nothing was queued that still reads the block
+        const std::string keep = g_err;
+        if (done) g_event_pool.push_back(done);
+        array_free(hold);
+        g_err = keep;
+    }
     return ok ? 0 : -1;
 }
 
@@ -742,7 +837,7 @@ int array_read_base(const NDArray* src, size_t offset, size_t count, f32* dst) {
 
 int array_write_base(NDArray* dst, size_t offset, size_t count, const f32* src) {
     AL_ENTER;
-    if (!valid(dst, "array_write_base")) return -1;
+    if (!valid_mut(dst, "array_write_base")) return -1;
     if (offset + count > dst->data->size) {
         set_error("IndexError: base write [%zu, %zu) exceeds %zu elements", offset, offset + count, dst->data->size);
         return -1;
@@ -784,7 +879,7 @@ f32 array_get_elem(const NDArray* a, const size_t* index) {
 NDArray* array_set_elem_from_scalar(NDArray* a, f32 value, const size_t* index) {
     AL_ENTER;
     size_t off;
-    if (!valid(a, "array_set_elem_from_scalar") || !flat_index(a, index, &off)) return nullptr;
+    if (!valid_mut(a, "array_set_elem_from_scalar") || !flat_index(a, index, &off)) return nullptr;
     if (!fill_const(a->ptr + off, 1, value)) return nullptr;
     return a;
 }

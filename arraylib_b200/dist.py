@@ -141,6 +141,45 @@ def reshard_plan(global_shape, perm, world: int) -> dict:
             "local_shape": (lead,) + new_shape[1:q] + (rows * world,) + new_shape[q + 1:]}
 
 
+def broadcast_shape(lhs, rhs) -> tuple:
+    """NumPy-style right-aligned broadcast of two shapes (arraylib.c:171-206); AssertionError like the reference's
+    Python layer (core.py:371-379) when they do not match."""
+    nd = max(len(lhs), len(rhs))
+    l = (1,) * (nd - len(lhs)) + tuple(lhs)
+    r = (1,) * (nd - len(rhs)) + tuple(rhs)
+    assert all(a == b or a == 1 or b == 1 for a, b in zip(l, r)), f"cannot broadcast shapes {tuple(lhs)} and {tuple(rhs)}"
+    return tuple(max(a, b) for a, b in zip(l, r))
+
+
+def binary_plan(operands, out_shape) -> dict:
+    """How `lhs o rhs` runs on sharded operands (pure planning). `operands`: (shape, placement, axis, bounds) each.
+    The output is cut along ITS leading non-unit axis with the bounds of the first operand that is already cut
+    there; every operand is then used as `block` (its local block as it is), `whole` (it is broadcast along that
+    axis) or `("rows", k)` (this rank's rows of its axis k, taken from a replica -- a sharded operand that is cut
+    along another axis or at other rows is gathered first). When no operand is cut along the output's shard axis
+    everything is computed replicated."""
+    nd = len(out_shape)
+    out_axis = shard_axis(out_shape)
+    bounds = None
+    for shape, placement, axis, b in operands:
+        k = out_axis - (nd - len(shape))
+        if placement == "sharded" and k == axis and shape[k] == out_shape[out_axis]:
+            bounds = tuple(b)
+            break
+    if bounds is None:
+        return {"output": "replicated", "operands": ["whole"] * len(operands)}
+    how = []
+    for shape, placement, axis, b in operands:
+        k = out_axis - (nd - len(shape))
+        if k < 0 or shape[k] == 1:
+            how.append("whole")
+        elif placement == "sharded" and k == axis and tuple(b) == bounds:
+            how.append("block")
+        else:
+            how.append(("rows", k))
+    return {"output": "sharded", "axis": out_axis, "bounds": bounds, "operands": how}
+
+
 def _count(shape) -> int:
     n = 1
     for e in shape:
@@ -271,6 +310,17 @@ def allreduce_scalar(value: float, op: str = "sum") -> float:
     box = core.full((4,), float(value))
     allreduce(box, op)
     return float(core.to_numpy(box)[0])
+
+
+def broadcast_scalar(value: float, src: int) -> float:
+    """The float32 `value` of rank `src` on every rank (bit pattern preserved: NaN payloads and -0.0 survive,
+    which a sum over zero-padded contributions would not guarantee)."""
+    from . import core
+
+    if _state["world"] == 1:
+        return float(value)
+    got = core.to_numpy(allgather(core.full((4,), float(value))))
+    return float(got[4 * src])
 
 
 def barrier() -> None:
@@ -438,7 +488,7 @@ class ShardedArray:
         return self.local[sl]  # a view of this rank's rows of the replica
 
     def _like(self, local, shape=None, placement=None, axis=None, bounds=None):
-        return ShardedArray(local, self.shape if shape is None else shape, placement or self.placement,
+        return type(self)(local, self.shape if shape is None else shape, placement or self.placement,
                             self.axis if axis is None else axis, self.bounds if bounds is None else bounds)
 
     def _binary(self, name: str, other, reverse: bool = False):
@@ -448,50 +498,40 @@ class ShardedArray:
             res = fn(other, self.local) if reverse else fn(self.local, other)
             return self._like(res)
         if isinstance(other, core.NDArray):
-            other = ShardedArray(other, other.shape, "replicated")
+            other = type(self)(other, other.shape, "replicated")
         assert isinstance(other, ShardedArray)
-        import numpy as np
-        out_shape = tuple(np.broadcast_shapes(self.shape, other.shape))
-        nd = len(out_shape)
-        sharded = [op for op in (self, other) if op.placement == "sharded"]
-        if not sharded:
-            res = fn(other.local, self.local) if reverse else fn(self.local, other.local)
-            return ShardedArray(res, out_shape, "replicated")
-        out_axis = sharded[0].axis + nd - sharded[0].ndim  # right-aligned broadcasting
-        for op in sharded:
-            assert op.axis + nd - op.ndim == out_axis and op.shape[op.axis] == out_shape[out_axis], \
-                "a sharded operand must span the output's shard axis"
-            assert op.bounds == sharded[0].bounds, "sharded operands must be cut at the same rows"
-            assert all(e == 1 for e in out_shape[:out_axis]), "the shard axis must stay the leading non-unit axis"
+        out_shape = broadcast_shape(self.shape, other.shape)
+        plan = binary_plan([(op.shape, op.placement, op.axis, op.bounds) for op in (self, other)], out_shape)
         locs = []
-        for op in (self, other):
-            if op.placement == "sharded":
+        for op, how in zip((self, other), plan["operands"]):
+            if how == "block":          # cut the same way as the output: the local block is the operand
                 locs.append(op.local)
-                continue
-            k = out_axis - (nd - op.ndim)  # the operand's own index of the output's shard axis
-            if k < 0 or op.shape[k] == 1:
-                locs.append(op.local)  # broadcast along the shard axis: the replica is used as it is
-            else:
-                lo, hi = sharded[0].bounds[_state["rank"]]
-                locs.append(op.local[tuple(slice(lo, hi) if i == k else slice(0, e) for i, e in enumerate(op.shape))])
+            elif how == "whole":        # broadcast along the output's shard axis (or nothing is sharded)
+                locs.append(op.gather())
+            else:                       # ("rows", k): this rank's rows of a replica (gathered first if need be)
+                lo, hi = plan["bounds"][_state["rank"]]
+                whole = op.gather()
+                locs.append(whole[tuple(slice(lo, hi) if i == how[1] else slice(0, e) for i, e in enumerate(op.shape))])
         a, b = locs
         res = fn(b, a) if reverse else fn(a, b)
-        return ShardedArray(res, out_shape, "sharded", out_axis, sharded[0].bounds)
+        if plan["output"] == "replicated":
+            return type(self)(res, out_shape, "replicated")
+        return type(self)(res, out_shape, "sharded", plan["axis"], plan["bounds"])
 
     def _reduce(self, op: str, dims, replicated: bool = False):
         from . import core
         dims = tuple(range(self.ndim)) if dims is None else tuple(dims)
         out_shape = tuple(1 if d in dims else e for d, e in enumerate(self.shape))
         if self.placement == "replicated":
-            return ShardedArray(getattr(core, f"reduce_{op}")(self.local, dims=dims), out_shape, "replicated")
+            return type(self)(getattr(core, f"reduce_{op}")(self.local, dims=dims), out_shape, "replicated")
         even = len({hi - lo for lo, hi in self.bounds}) == 1
         plan = reduce_plan(self.ndim, dims, self.axis, self.shape, _state["world"])
         if plan["collective"] == "reduce_scatter" and not replicated and even:
-            return ShardedArray(reduce_sharded(self.local, op, dims, output="sharded", axis=self.axis), out_shape, "sharded",
+            return type(self)(reduce_sharded(self.local, op, dims, output="sharded", axis=self.axis), out_shape, "sharded",
                                 plan["out_axis"])
         if plan["collective"]:
-            return ShardedArray(reduce_sharded(self.local, op, dims, axis=self.axis), out_shape, "replicated")
-        return ShardedArray(getattr(core, f"reduce_{op}")(self.local, dims=dims), out_shape, "sharded", self.axis, self.bounds)
+            return type(self)(reduce_sharded(self.local, op, dims, axis=self.axis), out_shape, "replicated")
+        return type(self)(getattr(core, f"reduce_{op}")(self.local, dims=dims), out_shape, "sharded", self.axis, self.bounds)
 
     def reduce_sum(self, *, dims=None, replicated=False): return self._reduce("sum", dims, replicated)
     def reduce_max(self, *, dims=None, replicated=False): return self._reduce("max", dims, replicated)
@@ -513,13 +553,13 @@ class ShardedArray:
         from . import core
         shape = tuple(shape)
         if self.placement == "replicated":
-            return ShardedArray(core.reshape(self.local, shape), shape, "replicated")
+            return type(self)(core.reshape(self.local, shape), shape, "replicated")
         plan = reshape_plan(self.shape, self.bounds, shape)
         if plan["how"] == "gather":
-            return ShardedArray(core.reshape(self.gather(), shape), shape, "replicated")
+            return type(self)(core.reshape(self.gather(), shape), shape, "replicated")
         lo, hi = plan["bounds"][_state["rank"]]
         local_shape = tuple(hi - lo if i == plan["axis"] else e for i, e in enumerate(shape))
-        return ShardedArray(core.reshape(self.local, local_shape), shape, "sharded", plan["axis"], plan["bounds"])
+        return type(self)(core.reshape(self.local, local_shape), shape, "sharded", plan["axis"], plan["bounds"])
 
     def as_strided(self, *, shape, stride):
         """Sliding windows over a sharded 1-D array: shape (n - w + 1, w), stride (1, 1) (config C5a). Rank r keeps
@@ -528,7 +568,7 @@ class ShardedArray:
         from . import core
         shape, stride = tuple(shape), tuple(stride)
         if self.placement == "replicated":
-            return ShardedArray(core.as_strided(self.local, shape, stride), shape, "replicated")
+            return type(self)(core.as_strided(self.local, shape, stride), shape, "replicated")
         n = self.shape[0]
         if not (self.ndim == 1 and len(shape) == 2 and stride == (1, 1) and shape[0] + shape[1] - 1 == n):
             raise NotImplementedError("as_strided of a sharded array supports stride-(1, 1) sliding windows over a 1-D "
@@ -538,7 +578,7 @@ class ShardedArray:
         view_bounds = window_view_bounds(self.bounds, w)
         lo, hi = self.bounds[me]
         if world == 1 or w == 1:
-            return ShardedArray(core.as_strided(self.local, (hi - lo - w + 1, w), stride), shape, "sharded", 0, view_bounds)
+            return type(self)(core.as_strided(self.local, (hi - lo - w + 1, w), stride), shape, "sharded", 0, view_bounds)
         heights = [h - l for l, h in self.bounds]
         if min(heights) < w - 1:
             raise NotImplementedError("sliding windows wider than a rank's block: gather() the array first")
@@ -548,7 +588,7 @@ class ShardedArray:
             base = self.local
         else:
             base = core.cat([self.local, heads[(slice((me + 1) * (w - 1), (me + 2) * (w - 1)),)]], [0])
-        return ShardedArray(core.as_strided(base, (rows, w), stride), shape, "sharded", 0, view_bounds)
+        return type(self)(core.as_strided(base, (rows, w), stride), shape, "sharded", 0, view_bounds)
 
     # -- re-sharding ---------------------------------------------------------------------------------
     def transpose(self, perm):
@@ -558,27 +598,27 @@ class ShardedArray:
         world, me = _state["world"], _state["rank"]
         new_shape = tuple(self.shape[p] for p in perm)
         if self.placement == "replicated":
-            return ShardedArray(core.transpose(self.local, perm), new_shape, "replicated")
+            return type(self)(core.transpose(self.local, perm), new_shape, "replicated")
         even = self.bounds == all_bounds(self.shape[self.axis], world)
         if self.axis != 0 or not even:  # unusual cuts: replicate, transpose, keep the own block of the new shard axis
             whole = core.transpose(self.gather(), perm)
             ax = shard_axis(new_shape)
             lo, hi = shard_bounds(new_shape[ax], me, world)
             sl = tuple(slice(lo, hi) if i == ax else slice(0, e) for i, e in enumerate(new_shape))
-            return ShardedArray(core.copy(whole[sl], deep=True), new_shape, "sharded", ax)
+            return type(self)(core.copy(whole[sl], deep=True), new_shape, "sharded", ax)
         plan = reshard_plan(self.shape, perm, world)
         if plan["how"] == "local":
-            return ShardedArray(core.transpose(self.local, perm), plan["shape"], "sharded", 0)
+            return type(self)(core.transpose(self.local, perm), plan["shape"], "sharded", 0)
         if plan["how"] == "gather":
             whole = core.transpose(allgather_ragged(self.local, self.shape[0]), perm)
             ax = shard_axis(plan["shape"])
             lo, hi = shard_bounds(plan["shape"][ax], me, world)
             sl = tuple(slice(lo, hi) if i == ax else slice(0, e) for i, e in enumerate(plan["shape"]))
-            return ShardedArray(core.copy(whole[sl], deep=True), plan["shape"], "sharded", ax)
+            return type(self)(core.copy(whole[sl], deep=True), plan["shape"], "sharded", ax)
         piece = core.copy(core.transpose(self.local, perm), deep=True)   # (new leading axis in full, ..., own rows at q, ...)
         got = alltoall(piece)                                              # block i = rank i's rows of MY leading block
         mixed = core.transpose(core.reshape(got, plan["recv_view"]), plan["interleave"])
-        return ShardedArray(core.reshape(mixed, plan["local_shape"]), plan["shape"], "sharded", 0)
+        return type(self)(core.reshape(mixed, plan["local_shape"]), plan["shape"], "sharded", 0)
 
     # -- materialisation ----------------------------------------------------------------------------
     def gather(self):

@@ -19,7 +19,9 @@ import tempfile
 import time
 
 
-def launch(nproc: int, argv: list, *, timeout: float | None = None, env_extra: dict | None = None) -> int:
+def launch(nproc: int, argv: list, *, timeout: float | None = None, env_extra: dict | None = None, quiet_workers: bool = False) -> int:
+    """Run `python argv...` once per rank. `quiet_workers`: only rank 0 keeps its stdout (SPMD scripts print the same
+    thing on every rank)."""
     rdzv = tempfile.mkdtemp(prefix="arraylib_b200_rdzv_")
     procs = []
     try:
@@ -28,7 +30,8 @@ def launch(nproc: int, argv: list, *, timeout: float | None = None, env_extra: d
             env.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(nproc), LOCAL_WORLD_SIZE=str(nproc),
                        MASTER_ADDR="127.0.0.1", MASTER_PORT=env.get("MASTER_PORT", "29511"), ARRAYLIB_RDZV_DIR=rdzv)
             env.update(env_extra or {})
-            procs.append(subprocess.Popen([sys.executable] + list(argv), env=env, start_new_session=True))
+            out = subprocess.DEVNULL if quiet_workers and rank > 0 else None
+            procs.append(subprocess.Popen([sys.executable] + list(argv), env=env, start_new_session=True, stdout=out))
         deadline = None if timeout is None else time.monotonic() + timeout
         status = 0
         live = set(range(nproc))
@@ -68,10 +71,13 @@ def main() -> None:
     ap = argparse.ArgumentParser(prog="python -m arraylib_b200.launch")
     ap.add_argument("--nproc", type=int, required=True)
     ap.add_argument("--timeout", type=float, default=None)
+    ap.add_argument("--quiet-workers", action="store_true", help="only rank 0 keeps its stdout")
+    ap.add_argument("--spmd", action="store_true", help="export ARRAYLIB_SPMD=1: `import arraylib` gives the sharded al.* front end (arraylib_b200.spmd)")
     ap.add_argument("script")
     ap.add_argument("args", nargs=argparse.REMAINDER)
     ns = ap.parse_args()
-    sys.exit(launch(ns.nproc, [ns.script] + ns.args, timeout=ns.timeout))
+    sys.exit(launch(ns.nproc, [ns.script] + ns.args, timeout=ns.timeout, quiet_workers=ns.quiet_workers,
+                    env_extra={"ARRAYLIB_SPMD": "1"} if ns.spmd else None))
 
 
 if __name__ == "__main__":

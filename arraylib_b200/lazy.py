@@ -12,7 +12,9 @@ than the kernel's limits (4 arrays, 8 steps) are flushed to a temporary and cont
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import threading
 
 from . import core
 from ._lib import BINOPS, UFUNCS, ArrayP, check_ptr, lib
@@ -94,7 +96,12 @@ class Expr:
     def __le__(self, o): return self._binary("le", o, False)
     def __gt__(self, o): return self._binary("gt", o, False)
     def __ge__(self, o): return self._binary("ge", o, False)
+    def __eq__(self, o): return self._binary("eq", o, False)
+    def __ne__(self, o): return self._binary("ne", o, False)
+    def __mod__(self, o): return self._binary("mod", o, False)      # C fmod, like the reference's array % array
+    def __rmod__(self, o): return self._binary("mod", o, True)
     def __rpow__(self, o): return self._binary("pow", o, True)
+    __hash__ = None  # == builds an expression, so instances cannot be dictionary keys
     def __neg__(self): return self.apply("neg")
     def __pos__(self): return self
     def __abs__(self): return self.apply("abs")
@@ -205,6 +212,11 @@ class TExpr:
     def __le__(self, o): return self._binary("le", o, False)
     def __gt__(self, o): return self._binary("gt", o, False)
     def __ge__(self, o): return self._binary("ge", o, False)
+    def __eq__(self, o): return self._binary("eq", o, False)
+    def __ne__(self, o): return self._binary("ne", o, False)
+    def __mod__(self, o): return self._binary("mod", o, False)      # C fmod (sign of the dividend), NOT Python's %
+    def __rmod__(self, o): return self._binary("mod", o, True)
+    __hash__ = None
     def __neg__(self): return self._unary("neg")
     def __pos__(self): return self
     def __abs__(self): return self._unary("abs")
@@ -231,17 +243,94 @@ class TExpr:
         return NotImplemented
 
 
-def trace_unary(fn, array):
-    """Try to record `fn` (a Python callable of one scalar) as an FP64 tape over `array`: arithmetic
-    operators, comparisons, abs/neg/ceil/floor and numpy ufuncs trace; `math.*` calls, branches on the
-    value and anything else do not. Returns the evaluated NDArray, or None when `fn` did not trace."""
-    trace = _Trace([array])
+_MATH_UNARY = {"sqrt": "sqrt", "exp": "exp", "log": "log", "sin": "sin", "cos": "cos", "tan": "tan", "asin": "asin",
+               "acos": "acos", "atan": "atan", "sinh": "sinh", "cosh": "cosh", "tanh": "tanh", "asinh": "asinh",
+               "acosh": "acosh", "atanh": "atanh", "fabs": "abs", "ceil": "ceil", "floor": "floor"}
+_MATH_BINARY = {"pow": "pow", "fmod": "mod"}
+_math_patch_lock = threading.RLock()
+
+
+@contextlib.contextmanager
+def _math_traceable():
+    """While a callable is being traced, `math.sqrt(x)` & co. must record an instruction instead of asking the
+    proxy for a float. The `math` module's functions are swapped for wrappers that do that for proxies and call
+    the original for everything else (so other threads keep working), and restored afterwards."""
+    import math
+    with _math_patch_lock:
+        saved = {}
+
+        def unary(name, op):
+            orig = saved[name]
+
+            def wrapper(x, *rest):
+                if isinstance(x, TExpr) and not rest:
+                    return x._unary(op)
+                return orig(x, *rest)
+            return wrapper
+
+        def binary(name, op):
+            orig = saved[name]
+
+            def wrapper(x, y):
+                if isinstance(x, TExpr):
+                    return x._binary(op, y, False)
+                if isinstance(y, TExpr):
+                    return y._binary(op, x, True)
+                return orig(x, y)
+            return wrapper
+
+        for name in list(_MATH_UNARY) + list(_MATH_BINARY):
+            saved[name] = getattr(math, name)
+        try:
+            for name, op in _MATH_UNARY.items():
+                setattr(math, name, unary(name, op))
+            for name, op in _MATH_BINARY.items():
+                setattr(math, name, binary(name, op))
+            yield
+        finally:
+            for name, orig in saved.items():
+                setattr(math, name, orig)
+
+
+def _run_traced(fn, n_inputs):
+    """(trace, result proxy) of `fn` called on `n_inputs` scalar proxies, or None when it does not trace
+    (data-dependent branch, builtin max/min, float(), unsupported operation, wrong return type)."""
+    trace = _Trace([None] * n_inputs)
     try:
-        out = fn(TExpr(trace, -1))
+        with _math_traceable():
+            out = fn(*[TExpr(trace, -1 - i) for i in range(n_inputs)])
     except (TypeError, NotImplementedError, AttributeError, ValueError):
         return None
     if not isinstance(out, TExpr) or out.trace is not trace:
         return None
+    return trace, out
+
+
+def single_instruction(fn, n_inputs):
+    """If `fn` traces to exactly ONE instruction over its distinct inputs (`lambda x: math.sqrt(x)`,
+    `lambda a, b: a + b`), return (kind, op name): kind 1 = unary ufunc, 0 = binary op. Else None."""
+    traced = _run_traced(fn, n_inputs)
+    if traced is None:
+        return None
+    trace, out = traced
+    if len(trace.insns) != 1 or out.src != 0:
+        return None
+    kind, op, a, b = trace.insns[0]
+    if kind == 1 and n_inputs == 1 and a[0] == -1:
+        return 1, UFUNCS[op]
+    if kind == 0 and n_inputs == 2 and {a[0], b[0]} == {-1, -2}:
+        return 0, BINOPS[op]
+    return None
+
+
+def trace_unary(fn, array):
+    """Try to record `fn` (a Python callable of one scalar) as an FP64 tape over `array`: arithmetic
+    operators, comparisons, abs/neg/ceil/floor, numpy ufuncs and `math.*` functions trace; branches on the
+    value, builtin max/min and anything else do not. Returns the evaluated NDArray, or None when `fn` did not trace."""
+    traced = _run_traced(fn, 1)
+    if traced is None:
+        return None
+    trace, out = traced
     if out.src < 0:  # the lambda returned its argument unchanged
         return core.copy(array, deep=True)
     insns = (TapeInsn * len(trace.insns))()

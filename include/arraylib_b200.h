@@ -85,6 +85,7 @@ int al_timer_stop(float* ms);        /* record + synchronize + elapsed milliseco
 int al_event_record(int idx);        /* record pooled event #idx on the library stream (no sync) */
 int al_event_elapsed(int first, int second, float* ms); /* waits for `second`, then the time between the two */
 uint64_t al_bytes_in_use(void);      /* device bytes currently held by live Data blocks */
+uint64_t al_bytes_cached(void);      /* idle bytes held by the block cache (bounded by the cache_limit_mb tuning knob, default half the device) */
 int al_trim_pool(void);              /* return cached pool memory to the driver */
 void* al_host_alloc(size_t bytes);   /* pinned host memory for staging */
 int al_host_free(void* p);

@@ -138,3 +138,83 @@ def test_reshard_plan_reproduces_the_global_transpose(world, shape, perm):
     for r in range(world):
         lo, hi = dist.shard_bounds(want.shape[0], r, world)
         np.testing.assert_array_equal(got[r], want[lo:hi])
+
+
+# ---- SPMD front end (arraylib_b200.spmd): pure planning ----------------------------------------------------
+
+
+def test_binary_plan_covers_block_whole_rows_and_the_replicated_fallback():
+    b8 = dist.all_bounds(1024, 8)
+    A = ((1024, 1, 4096), "sharded", 0, b8)
+    B = ((1, 1024, 4096), "replicated", 1, dist.all_bounds(1024, 8))
+    c = ((4096,), "replicated", 0, dist.all_bounds(4096, 8))
+    plan = dist.binary_plan([A, B], (1024, 1024, 4096))  # config C3: A's blocks, B whole
+    assert plan == {"output": "sharded", "axis": 0, "bounds": b8, "operands": ["block", "whole"]}
+    t = ((1024, 1024, 4096), "sharded", 0, b8)
+    assert dist.binary_plan([t, c], (1024, 1024, 4096))["operands"] == ["block", "whole"]
+    # a replica that spans the shard axis contributes this rank's rows
+    full = ((1024, 1024, 4096), "replicated", 0, b8)
+    assert dist.binary_plan([t, full], (1024, 1024, 4096))["operands"] == ["block", ("rows", 0)]
+    # B cut along ITS leading non-unit axis (axis 1) while the output is cut along axis 0: gathered, used whole
+    Bs = ((1, 1024, 4096), "sharded", 1, b8)
+    assert dist.binary_plan([A, Bs], (1024, 1024, 4096))["operands"] == ["block", "whole"]
+    # same axis, other rows (uneven cut): the second operand goes through a replica
+    odd = tuple((lo + (1 if lo else 0), hi + (1 if hi < 1024 else 0)) for lo, hi in b8)
+    t2 = ((1024, 1024, 4096), "sharded", 0, odd)
+    assert dist.binary_plan([t, t2], (1024, 1024, 4096))["operands"] == ["block", ("rows", 0)]
+    # [N,1] + [N] -> [N,N]: the output's shard axis is axis 0, the 1-D operand spans axis 1 only
+    col, row = ((512, 1), "sharded", 0, dist.all_bounds(512, 2)), ((512,), "sharded", 0, dist.all_bounds(512, 2))
+    assert dist.binary_plan([col, row], (512, 512))["operands"] == ["block", ("rows", 1)] or \
+        dist.binary_plan([col, row], (512, 512))["operands"] == ["block", "whole"]
+    # nothing is cut along the output's shard axis: replicated
+    assert dist.binary_plan([B, c], (1, 1024, 4096))["output"] == "replicated"
+
+
+def test_broadcast_shape_matches_numpy_and_rejects_like_the_reference():
+    for lhs, rhs in [((3, 1, 5), (4, 5)), ((1,), (7, 2)), ((6, 1), (1, 6)), ((2, 3, 4), (2, 3, 4))]:
+        assert dist.broadcast_shape(lhs, rhs) == tuple(np.broadcast_shapes(lhs, rhs))
+    with pytest.raises(AssertionError):
+        dist.broadcast_shape((3, 4), (5,))
+
+
+def test_spmd_placement_policy_and_strided_rows():
+    from arraylib_b200 import spmd
+    assert spmd.placement_for((1024, 1, 4096), 8, 1 << 20) == "sharded"
+    assert spmd.placement_for((3, 4), 8, 1 << 20) == "replicated"          # small
+    assert spmd.placement_for((4, 1 << 20), 8, 1 << 20) == "replicated"    # fewer rows than ranks
+    assert spmd.placement_for((1, 1, 64, 1 << 16), 8, 1 << 20) == "sharded"  # leading unit axes are skipped
+    assert spmd.placement_for((1 << 24,), 1, 0) == "replicated"            # one rank
+    # rows 1, 4, 7, ... < 20 split over blocks [0,5) [5,12) [12,20)
+    seq = list(range(1, 20, 3))
+    seen = []
+    for lo, hi in ((0, 5), (5, 12), (12, 20)):
+        got = spmd.strided_rows_in_block(1, 20, 3, lo, hi)
+        k0, k1, l0, l1 = got
+        rows = list(range(lo + l0, lo + l1, 3))
+        assert rows == seq[k0:k1] and all(lo <= r < hi for r in rows)
+        seen += rows
+    assert seen == seq
+    assert spmd.strided_rows_in_block(0, 4, 1, 8, 16) is None
+    assert spmd.strided_rows_in_block(10, 40, 16, 0, 10) is None
+    assert spmd.owner_of(5, ((0, 5), (5, 12))) == 1
+    # exhaustive against numpy index arithmetic
+    for start, end, step in [(0, 33, 1), (2, 31, 5), (7, 8, 3), (0, 64, 64), (5, 60, 7)]:
+        want = list(range(start, end, step))
+        got = []
+        for lo, hi in dist.all_bounds(64, 5):
+            r = spmd.strided_rows_in_block(start, end, step, lo, hi)
+            if r:
+                assert want[r[0]:r[1]] == list(range(lo + r[2], lo + r[3], step))
+                got += want[r[0]:r[1]]
+        assert got == want
+
+
+def test_shim_selects_the_spmd_front_end_only_on_request(monkeypatch):
+    import importlib
+    import arraylib
+    assert arraylib.NDArray.__module__ == "arraylib_b200.core"   # default: single device, even under torchrun
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.delenv("ARRAYLIB_SPMD", raising=False)
+    assert importlib.reload(arraylib).NDArray.__module__ == "arraylib_b200.core"
+    monkeypatch.delenv("WORLD_SIZE")
+    importlib.reload(arraylib)

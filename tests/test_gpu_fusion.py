@@ -112,12 +112,19 @@ def test_apply_resolution_order_and_refusals(al):
     from arraylib_b200._lib import lib
     al.apply(math.sqrt, a)
     assert lib.al_last_kernel() in (b"ew_nd_vec4", b"ew_nd_scalar")  # named ufunc, not a chain
-    al.apply(lambda v: math.sqrt(v), a)  # math.* cannot be traced -> probe fingerprint -> named ufunc
+    al.apply(lambda v: math.sqrt(v), a)  # traces to exactly one ufunc -> the named kernel
     assert lib.al_last_kernel() in (b"ew_nd_vec4", b"ew_nd_scalar")
     with pytest.raises(NotImplementedError):
         al.apply(lambda v: v if v > 3 else 0.0, a)  # data-dependent branch
     with pytest.raises(NotImplementedError):
-        al.apply(lambda v: math.sqrt(v) + 1.0, a)  # math.* inside a composite expression
+        al.apply(lambda v: math.exp(min(v, 50)), a)  # builtin min branches on the value: refused, never guessed
+    x = np.arange(1, 25, dtype=np.float32).reshape(4, 6)
+    got = al.to_numpy(al.apply(lambda v: math.sqrt(v) + 1.0, a))  # math.* inside a composite expression: FP64 tape
+    want = np.array([math.sqrt(float(v)) + 1.0 for v in x.ravel()], dtype=np.float64).astype(np.float32).reshape(4, 6)
+    assert_bit_equal(got, want, "sqrt + 1 tape")
+    got = al.to_numpy(al.apply(lambda v: v * (v != 3) + (v == 5) * 100.0 + v % 4, a))
+    want = np.array([v * (v != 3) + (v == 5) * 100.0 + math.fmod(v, 4) for v in x.ravel().astype(np.float64)]).astype(np.float32).reshape(4, 6)
+    assert_bit_equal(got, want, "eq / ne / mod tape")
 
 
 def test_apply_lambdas_against_reference_golden(al):

@@ -28,12 +28,54 @@ def test_unary_unresolvable_raises(fn):
 
 @pytest.mark.parametrize("fn,name", [
     (lambda x, y: x + y, "sum"), (operator.add, "sum"), (max, "max"), (min, "min"), (np.maximum, "max"),
-    (lambda a, b: a * b, "prod"), (lambda a, b: a if a > b else b, "max"), (np.add, "sum"), ("min", "min"),
+    (lambda a, b: a * b, "prod"), (lambda a, b: np.maximum(a, b), "max"), (lambda acc, v: v + acc, "sum"), (np.add, "sum"), ("min", "min"),
 ])
 def test_reduce_resolution(fn, name):
     assert REDOPS[ufuncs.resolve_reduce(fn)] == name
 
 
-def test_reduce_unresolvable_raises():
+@pytest.mark.parametrize("fn", [
+    lambda a, b: a - b,                      # not an accumulator the device has
+    lambda a, b: a if a > b else b,          # data-dependent branch: cannot be traced, and is NOT guessed from samples
+    lambda a, b: max(a, b),                  # builtin max compares and branches
+    lambda a, b: a + b + 0.0,                # two instructions
+    lambda a, b: a + a,                      # ignores one argument
+])
+def test_reduce_unresolvable_raises(fn):
     with pytest.raises(NotImplementedError):
-        ufuncs.resolve_reduce(lambda a, b: a - b)
+        ufuncs.resolve_reduce(fn)
+
+
+@pytest.mark.parametrize("fn", [
+    lambda x: math.exp(min(x, 50)),                      # equals exp on any small probe set, differs for x > 50
+    lambda x: math.sqrt(x) if x < 100 else 10.0,         # piecewise
+    lambda x: math.sqrt(float(x)),                       # float() of the proxy
+])
+def test_piecewise_callables_are_refused_not_guessed(fn):
+    with pytest.raises(NotImplementedError):
+        ufuncs.resolve_unary(fn)
+
+
+def test_math_module_is_restored_after_tracing():
+    before = (math.sqrt, math.exp, math.pow, math.fmod, math.floor)
+    ufuncs.resolve_unary(lambda x: math.sqrt(x))
+    with pytest.raises(NotImplementedError):
+        ufuncs.resolve_unary(lambda x: math.sqrt(x) if x > 0 else 0.0)
+    assert (math.sqrt, math.exp, math.pow, math.fmod, math.floor) == before
+    assert math.sqrt(4.0) == 2.0
+
+
+def test_traced_comparisons_and_mod_build_instructions():
+    """`x == c` / `x != c` / `x % c` inside a traced lambda must become tape instructions, not Python
+    bools baked in as constants."""
+    import importlib
+    lazy = importlib.import_module("arraylib_b200.lazy")  # (the package attribute `lazy` is the function)
+    from arraylib_b200._lib import BINOPS
+    for fn, op in ((lambda x: x == 2, "eq"), (lambda x: x != 0, "ne"), (lambda x: x % 3, "mod"), (lambda x: 7 % x, "mod"),
+                   (lambda x: math.fmod(x, 3), "mod"), (lambda x: math.pow(x, 2), "pow")):
+        trace, out = lazy._run_traced(fn, 1)
+        assert len(trace.insns) == 1 and trace.insns[0][0] == 0 and BINOPS[trace.insns[0][1]] == op
+    trace, out = lazy._run_traced(lambda x: x * (x != 0), 1)
+    assert [BINOPS[i[1]] for i in trace.insns] == ["ne", "mul"]
+    with pytest.raises(TypeError):
+        hash(lazy.TExpr(trace, -1))
