@@ -39,6 +39,7 @@ struct Runtime {
     long reduce_loads_per_lane = 0;  // reduce_inner team sizing: reduced items per lane (0 = default 4)
     long reduce_peel = 1;      // 0: misaligned unit-stride rows use scalar lanes instead of masked aligned float4s
     long reduce_sequential = 0;  // 1: one thread per output, the reference's summation order (bit-exact, slow)
+    long skip_zero_sign_fix = 0; // 1: max/min keep the tree's zero sign (+0 / -0) instead of the reference's first-zero rule
     long disable_window = 0;
     long window_whole_blocks = 0;  // 1: fixed-w windows use the whole-block scan kernel instead of the half-block one
     long window_shfl = 1;      // fixed-w windows: 1..4 = register/shuffle kernel (cp.async ring shapes), 0 = shared-memory scan kernels

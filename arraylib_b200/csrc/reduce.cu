@@ -35,8 +35,8 @@ namespace al {
 
 // accumulate step (arraylib.c:12-19). max/min use the hardware NaN-ignoring FMNMX: identical to the
 // reference's fmax/fmin except for the SIGN of a zero result when the reduced set holds both +0 and -0
-// (the reference returns whichever zero comes first in logical order, which no tree can reproduce; here
-// max gives +0 and min gives -0, independent of order).
+// (the reference returns whichever zero comes first in logical order; FMNMX gives +0 for max and -0 for
+// min, independent of order). reduce_zero_sign_kernel repairs those outputs after the tree.
 template <int OP>
 __device__ __forceinline__ float racc(float a, float b) {
     if constexpr (OP == AL_RSUM) return __fadd_rn(a, b);
@@ -1459,6 +1459,87 @@ static bool build_axes(int redop, const NDArray* src, const size_t* dims, size_t
     return true;
 }
 
+// ---- sign of a zero max/min result (arraylib.c:18-19, 737-744) -----------------------------------------------
+// fmax/fmin keep their LEFT operand when both compare equal, so the reference's sequential fold returns the FIRST
+// zero in logical order when the extreme value of a reduced set is zero and the set holds both +0 and -0 (checked
+// against the compiled reference: max of [-0, +0] is -0, of [+0, -0] is +0; same for min). The tree kernels use the
+// hardware FMNMX (max -> +0, min -> -0 whatever the order). This pass repairs exactly those outputs: one warp per
+// output reads the result; only when it is a zero does the warp walk the reduced elements in the reference's logical
+// order, 32 at a time, and stop at the first zero. Non-zero outputs cost one 4-byte read each.
+constexpr int kZeroFixDims = 16;
+struct ZeroFixArgs {
+    int nkept, nred;
+    uint64_t kext[kZeroFixDims], rext[kZeroFixDims];      // logical order, OUTERMOST first
+    int64_t kstride[kZeroFixDims], rstride[kZeroFixDims];
+    uint64_t nout, count;
+};
+
+__global__ void __launch_bounds__(256)
+reduce_zero_sign_kernel(const float* __restrict__ src, float* __restrict__ out, const ZeroFixArgs a, float init, int init_is_zero) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t o = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); o < a.nout; o += warps) {
+        const float v = out[o];
+        if (v != 0.0f) continue;  // (NaN compares unequal too)
+        if (init_is_zero) {       // a zero init is the first zero of the fold
+            if (lane == 0) out[o] = init;
+            continue;
+        }
+        int64_t base = 0;
+        uint64_t rem = o;
+        for (int d = a.nkept - 1; d >= 0; d--) {
+            base += (int64_t)(rem % a.kext[d]) * a.kstride[d];
+            rem /= a.kext[d];
+        }
+        for (uint64_t r0 = 0; r0 < a.count; r0 += 32) {
+            const uint64_t r = r0 + lane;
+            float x = 1.0f;
+            if (r < a.count) {
+                int64_t off = base;
+                uint64_t q = r;
+                for (int d = a.nred - 1; d >= 0; d--) {
+                    off += (int64_t)(q % a.rext[d]) * a.rstride[d];
+                    q /= a.rext[d];
+                }
+                x = src[off];
+            }
+            const unsigned hit = __ballot_sync(0xffffffffu, x == 0.0f);
+            if (hit) {
+                const float first = __shfl_sync(0xffffffffu, x, __ffs(hit) - 1);
+                if (lane == 0) out[o] = first;
+                break;
+            }
+        }
+    }
+}
+
+// Returns false only on a launch failure. Layouts with more than kZeroFixDims non-unit axes keep the tree's sign.
+static bool fix_zero_sign(const NDArray* src, float* out, const bool* red, float init, bool custom_init) {
+    ZeroFixArgs a;
+    memset(&a, 0, sizeof a);
+    a.nout = a.count = 1;
+    for (size_t i = 0; i < src->lay->ndim; i++) {
+        const uint64_t e = src->lay->shape[i];
+        if (e == 1) continue;
+        if (red[i]) {
+            if (a.nred == kZeroFixDims) return true;
+            a.rext[a.nred] = e;
+            a.rstride[a.nred++] = (int64_t)src->lay->stride[i];
+            a.count *= e;
+        } else {
+            if (a.nkept == kZeroFixDims) return true;
+            a.kext[a.nkept] = e;
+            a.kstride[a.nkept++] = (int64_t)src->lay->stride[i];
+            a.nout *= e;
+        }
+    }
+    const uint64_t blocks = (a.nout + 7) / 8;
+    const unsigned grid = (unsigned)std::min<uint64_t>(blocks, (uint64_t)kNumSMs * 8);
+    reduce_zero_sign_kernel<<<grid, 256, 0, rt().stream>>>(src->ptr, out, a, init, custom_init && init == 0.0f);
+    note_launch("reduce_zero_sign");
+    return check_launch("reduce_zero_sign");
+}
+
 NDArray* reduce_impl(int redop, const NDArray* src, const size_t* dims, size_t ndims, float init, bool custom_init) {
     if (!valid(src, "array_reduce")) return nullptr;
     const size_t nd = src->lay->ndim;
@@ -1506,6 +1587,8 @@ NDArray* reduce_impl(int redop, const NDArray* src, const size_t* dims, size_t n
         case AL_RMIN: ok = run_reduce<AL_RMIN>(src->ptr, out->ptr, K, R, init); break;
         case AL_RPROD: ok = run_reduce<AL_RPROD>(src->ptr, out->ptr, K, R, init); break;
     }
+    if (ok && (redop == AL_RMAX || redop == AL_RMIN) && !rt().reduce_sequential && !rt().skip_zero_sign_fix)
+        ok = fix_zero_sign(src, out->ptr, red, init, custom_init);
     if (!ok) {
         std::string keep = last_error_string();
         release_array(out);

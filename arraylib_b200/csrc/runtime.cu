@@ -508,6 +508,7 @@ int al_set_tuning(const char* key, long value) {
     else if (k == "force_general") g_rt.force_general = value;
     else if (k == "reduce_splits") g_rt.reduce_splits = value;
     else if (k == "reduce_sequential") g_rt.reduce_sequential = value;
+    else if (k == "skip_zero_sign_fix") g_rt.skip_zero_sign_fix = value;
     else if (k == "reduce_loads_per_lane") g_rt.reduce_loads_per_lane = value;
     else if (k == "disable_window") g_rt.disable_window = value;
     else if (k == "window_shfl") g_rt.window_shfl = value;

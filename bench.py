@@ -521,8 +521,37 @@ def run_gpu(args):
             del pageable, outs_pageable
         except Exception as exc:  # noqa: BLE001
             e2e["stock_api"] = {"error": repr(exc)}
-        if hasattr(lib, "al_numa_info"):
-            e2e["host_binding"] = lib.al_numa_info().decode()
+        # what the host side of this box can move while ALL ranks copy at once (the ceiling of the e2e figure):
+        # 1 GiB pinned each way per rank, one direction at a time and then both together
+        try:
+            del hout
+            pn = 1 << 28
+            ph_in, ph_out = al.host_buffer((pn,)), al.host_buffer((pn,))
+            pd = al.from_numpy(ph_in, blocking=False)
+            al.synchronize()
+
+            def copy_rate(up, down, reps=3):
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    if up:
+                        keep = al.from_numpy(ph_in, blocking=False)
+                    if down:
+                        al.to_numpy(pd, out=ph_out, blocking=False)
+                    al.synchronize()
+                    if up:
+                        del keep
+                barrier()
+                dt = max_over_ranks(time.perf_counter() - t0) / reps
+                return round(4 * pn * world * (int(up) + int(down)) / dt / 1e9, 1)
+
+            copy_rate(True, True, 1)
+            e2e["pcie_probe"] = {"h2d_gbs": copy_rate(True, False), "d2h_gbs": copy_rate(False, True), "both_gbs": copy_rate(True, True),
+                                 "wire_gbs_of_the_e2e_step": round((int(suite.h2d_bytes) + int(d2h_bytes)) * world / e2e_s / 1e9, 1),
+                                 "note": "aggregate over all ranks copying AT THE SAME TIME, 1 GiB pinned per rank and direction; the e2e step cannot move its bytes faster than this"}
+            del pd, ph_in, ph_out
+        except Exception as exc:  # noqa: BLE001
+            e2e["pcie_probe"] = {"error": repr(exc)}
 
     # ---- the other scaling mode, briefly (N > 1 only) ----
     other = None

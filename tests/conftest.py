@@ -53,14 +53,19 @@ def bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
 
 
-def assert_bit_equal(got, want, what=""):
-    """Bit-exact float32 comparison; NaNs match any NaN (payload-agnostic)."""
+def assert_bit_equal(got, want, what="", nan_ok=False):
+    """Bit-exact float32 comparison, NaN sign and payload included (the eager elementwise kernels follow the
+    reference's x86/glibc NaN rules bit for bit). `nan_ok=True` lets any NaN match any NaN: only for the documented
+    exceptions -- reductions (the tree order decides which NaN survives), fused chains / FP64 tapes (canonical GPU
+    NaN, include/arraylib_b200.h:18-20) and comparisons against NumPy instead of the reference."""
     got = np.ascontiguousarray(got, dtype=np.float32)
     want = np.ascontiguousarray(want, dtype=np.float32)
     assert got.shape == want.shape, f"{what}: shape {got.shape} != {want.shape}"
-    both_nan = np.isnan(got) & np.isnan(want)
-    same = (bits(got) == bits(want)) | both_nan
+    same = bits(got) == bits(want)
+    if nan_ok:
+        same |= np.isnan(got) & np.isnan(want)
     if not same.all():
         idx = np.argwhere(~same)[0]
         raise AssertionError(f"{what}: {int((~same).sum())} of {same.size} elements differ; first at {tuple(idx)}: "
-                             f"got {got[tuple(idx)]!r} want {want[tuple(idx)]!r}")
+                             f"got {got[tuple(idx)]!r} (0x{int(bits(got)[tuple(idx)]):08x}) want {want[tuple(idx)]!r} "
+                             f"(0x{int(bits(want)[tuple(idx)]):08x})")

@@ -91,3 +91,58 @@ def test_c5b_transposed_add_and_copy_16384(al, rng):
     flat = xt.reshape((m * m,))
     assert not flat.view
     assert_bit_equal(al.to_numpy(flat), np.ascontiguousarray(x.T).reshape(-1), "X.T.reshape")
+
+
+def test_c4_reduce_sum_normal_data_within_the_stated_tolerance(al, orc, ref, rng):
+    """VERDICT r1 weak #1a: float reduce_sum at the FULL C4 size on normally distributed data (not small integers).
+    Stated tolerance: |gpu - ref| <= 2 n 2^-24 sum|x| with n the reduced elements per output,
+    ref = the serial reference's sum in its own order, and the GPU result is at least as close to the exact (float64)
+    sum as the reference is, up to 2^-22 |exact| + tol/2. n = 2^18 for dims (1,2): the longest reduced extent of
+    the suite."""
+    shape = (64, 512, 512, 64)
+    x = fast_normal(rng, int(np.prod(shape))).reshape(shape)
+    X = al.from_numpy(x)
+    eps = 2.0 ** -24
+    for dims in ((1, 2), (3,), (0,)):
+        n = int(np.prod([shape[d] for d in dims]))
+        got = al.to_numpy(al.reduce_sum(X, dims=dims)).astype(np.float64)
+        exact = x.sum(axis=dims, keepdims=True, dtype=np.float64)
+        sabs = np.abs(x).sum(axis=dims, keepdims=True, dtype=np.float64)
+        if ref is not None:
+            serial = ref.reduce("sum", ref.from_numpy(x), dims).numpy().astype(np.float64)
+        else:
+            serial = orc.reduce("sum", x, dims).astype(np.float64)
+        tol = 2 * n * eps * sabs
+        assert (np.abs(got - serial) <= tol).all(), f"dims {dims}: |gpu - ref| exceeds 2 n eps sum|x|"
+        assert (np.abs(got - exact) <= np.abs(serial - exact) + 2.0 ** -22 * np.abs(exact) + tol / 2).all()
+        # what the tree actually achieves, in units of eps * sum|x| (a pairwise tree is O(log n), the serial loop O(n))
+        gpu_err = float((np.abs(got - exact) / (eps * sabs)).max())
+        ref_err = float((np.abs(serial - exact) / (eps * sabs)).max())
+        print(f"C4 reduce_sum dims={dims} n={n}: max |err| / (eps sum|x|): gpu {gpu_err:.3f}, serial reference {ref_err:.3f}")
+        assert gpu_err <= 2 * np.log2(n) + 2
+
+
+def test_c5a_sliding_window_2p28_normal_data(al, orc, rng):
+    """Same for the 2^28-element sliding-window view (n = 64 per output): exact float64 sums through a float64 prefix
+    sum for every output, and the reference's own serial order on 16 sampled stretches of 2^16 windows."""
+    n, w = 1 << 28, 64
+    base = fast_normal(rng, n)
+    got = al.to_numpy(al.from_numpy(base).as_strided(shape=(n - w + 1, w), stride=(1, 1)).reduce_sum(dims=[1])).reshape(-1)
+    eps = 2.0 ** -24
+    csum = np.concatenate([[0.0], np.cumsum(base, dtype=np.float64)])
+    exact = csum[w:] - csum[:-w]
+    cabs = np.concatenate([[0.0], np.cumsum(np.abs(base), dtype=np.float64)])
+    sabs = cabs[w:] - cabs[:-w]
+    slack = 2.0 ** -52 * 4 * cabs[-1]  # the float64 prefix sums themselves
+    assert (np.abs(got - exact) <= 2 * w * eps * sabs + slack).all()
+    worst = 0.0
+    for start in rng.integers(0, n - (1 << 16) - w, size=16):
+        start = int(start)
+        seg = base[start:start + (1 << 16) + w - 1]
+        win = np.lib.stride_tricks.as_strided(seg, shape=(1 << 16, w), strides=(4, 4))
+        serial = orc.reduce("sum", win, (1,)).reshape(-1).astype(np.float64)
+        mine = got[start:start + (1 << 16)]
+        bound = 2 * w * eps * sabs[start:start + (1 << 16)]
+        assert (np.abs(mine - serial) <= bound).all()
+        worst = max(worst, float((np.abs(mine - exact[start:start + (1 << 16)]) / (eps * sabs[start:start + (1 << 16)] + 1e-300)).max()))
+    print(f"C5a window sums: max |gpu - exact| / (eps sum|x|) on the sampled stretches: {worst:.3f}")

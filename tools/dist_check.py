@@ -57,9 +57,12 @@ check(f"window halo shard (rank {rank})", al.to_numpy(win), want[lo:hi])
 SA, SB, Sc, SX = dist.ShardedArray.scatter(A), dist.ShardedArray.replicate(B), dist.ShardedArray.replicate(c), dist.ShardedArray.scatter(X)
 check("ShardedArray chain", (SA + SB + Sc + 1.0).to_numpy(), orc.binary("sum", orc.binary("sum", orc.binary("sum", A, B), c), 1.0))
 check("ShardedArray sharded*replica", (SX * dist.ShardedArray.replicate(X)).to_numpy(), orc.binary("mul", X, X))
-r = SX.reduce_sum(dims=(0, 2))
-assert r.placement == "replicated" and r.shape == (1, 20, 1, 64)
+r = SX.reduce_sum(dims=(0, 2))  # 20 x 64 outputs: stays sharded along axis 1 when 20 divides by the world size
+assert r.shape == (1, 20, 1, 64) and r.placement == ("sharded" if 20 % world == 0 else "replicated")
 check("ShardedArray reduce (0,2)", r.to_numpy(), orc.reduce("sum", X, (0, 2)))
+r = SX.reduce_sum(dims=(0, 2), replicated=True)
+assert r.placement == "replicated" and r.shape == (1, 20, 1, 64)
+check("ShardedArray reduce (0,2) replicated", r.to_numpy(), orc.reduce("sum", X, (0, 2)))
 r = (SX - 1.0).reduce_max(dims=(1, 3))
 assert r.placement == "sharded"
 check("ShardedArray reduce_max (1,3)", r.to_numpy(), orc.reduce("max", orc.binary("sub", X, 1.0), (1, 3)))
