@@ -50,6 +50,7 @@ struct Runtime {
     long stream_tma = 0;       // 1: contiguous add/mul through the cp.async.bulk + mbarrier pipeline (experiment)
     long interleave = 1;       // 0: short-axis transposes always use the rectangular tile kernel
     long outer_tile = 1;       // 0: do not use the register-tiled outer-broadcast kernel
+    long host_staging = 1;     // 0: pageable from_numpy / to_numpy use plain cudaMemcpy instead of the library's pinned ring + copy threads
     long peer_collective = 1;  // 0: cross-GPU reductions go through ncclAllReduce instead of the peer-memory windows
 };
 Runtime& rt();

@@ -32,8 +32,11 @@ struct ChainArgs {
 // One chain step over N lanes. The op is decoded ONCE (the switch is outside the lane loops), so the
 // interpreter costs a handful of instructions per step per thread, not per element. The steps use the
 // *_raw functions: a fused chain is issue-bound, and the per-element NaN fix-up of the eager kernels
-// (x86 sign and payload, elementwise.cuh) cost 2.5 -> 6.0 ms on the C3 chain. Every non-NaN result is
-// bit-identical to the eager path; a NaN result is the GPU's canonical NaN.
+// (x86 sign and payload, elementwise.cuh) after EVERY step cost 2.5 -> 6.0 ms on the C3 chain. Instead the
+// fix-up is deferred: every non-NaN final result is bit-identical to the eager path whatever happened to NaNs on
+// the way (max/min and the comparisons swallow a NaN the same way for any payload), and an element whose FINAL
+// value is a NaN (one compare per element) is replayed from its operands by chain_exact() with the eager
+// kernels' *_apply functions -- so a chain returns the reference's NaN sign and payload too.
 template <int OP, int N>
 __device__ __forceinline__ void lanes_bin(float* acc, const float* other, bool reversed) {
     if (reversed) {
@@ -104,6 +107,70 @@ __device__ __forceinline__ void chain_step(float* acc, const float* other, int k
     }
 }
 
+template <int OP>
+__device__ __forceinline__ float bin_exact_dir(float acc, float other, bool rev) {
+    return rev ? binop_apply<OP>(other, acc) : binop_apply<OP>(acc, other);
+}
+__device__ __noinline__ float chain_exact_step(float acc, float other, int kind, int op) {
+    if (kind == CH_UNARY) {
+        switch (op) {
+            case AL_NEG: return ufunc_apply<AL_NEG>(acc);
+            case AL_ABS: return ufunc_apply<AL_ABS>(acc);
+            case AL_SQRT: return ufunc_apply<AL_SQRT>(acc);
+            case AL_CEIL: return ufunc_apply<AL_CEIL>(acc);
+            case AL_FLOOR: return ufunc_apply<AL_FLOOR>(acc);
+            case AL_EXP: return ufunc_apply<AL_EXP>(acc);
+            case AL_LOG: return ufunc_apply<AL_LOG>(acc);
+            case AL_SIN: return ufunc_apply<AL_SIN>(acc);
+            case AL_COS: return ufunc_apply<AL_COS>(acc);
+            case AL_TAN: return ufunc_apply<AL_TAN>(acc);
+            case AL_ASIN: return ufunc_apply<AL_ASIN>(acc);
+            case AL_ACOS: return ufunc_apply<AL_ACOS>(acc);
+            case AL_ATAN: return ufunc_apply<AL_ATAN>(acc);
+            case AL_SINH: return ufunc_apply<AL_SINH>(acc);
+            case AL_COSH: return ufunc_apply<AL_COSH>(acc);
+            case AL_TANH: return ufunc_apply<AL_TANH>(acc);
+            case AL_ASINH: return ufunc_apply<AL_ASINH>(acc);
+            case AL_ACOSH: return ufunc_apply<AL_ACOSH>(acc);
+            default: return ufunc_apply<AL_ATANH>(acc);
+        }
+    }
+    const bool rev = (kind == CH_IN_ACC || kind == CH_SCALAR_ACC);
+    switch (op) {
+        case AL_SUM: return bin_exact_dir<AL_SUM>(acc, other, rev);
+        case AL_SUB: return bin_exact_dir<AL_SUB>(acc, other, rev);
+        case AL_MUL: return bin_exact_dir<AL_MUL>(acc, other, rev);
+        case AL_DIV: return bin_exact_dir<AL_DIV>(acc, other, rev);
+        case AL_MOD: return bin_exact_dir<AL_MOD>(acc, other, rev);
+        case AL_POW: return bin_exact_dir<AL_POW>(acc, other, rev);
+        case AL_MAX: return bin_exact_dir<AL_MAX>(acc, other, rev);
+        case AL_MIN: return bin_exact_dir<AL_MIN>(acc, other, rev);
+        case AL_EQ: return bin_exact_dir<AL_EQ>(acc, other, rev);
+        case AL_NE: return bin_exact_dir<AL_NE>(acc, other, rev);
+        case AL_GT: return bin_exact_dir<AL_GT>(acc, other, rev);
+        case AL_GE: return bin_exact_dir<AL_GE>(acc, other, rev);
+        case AL_LT: return bin_exact_dir<AL_LT>(acc, other, rev);
+        default: return bin_exact_dir<AL_LE>(acc, other, rev);
+    }
+}
+
+// Replays ONE element's chain with the eager kernels' NaN rules (slow path: only for elements whose fast result is a NaN).
+template <int NIN>
+__device__ __noinline__ float chain_exact(const ChainArgs<NIN>& ca, float v0, float v1, float v2, float v3) {
+    float acc = v0;
+    int next = 1;
+    for (int s = 0; s < ca.n_steps; s++) {
+        const int kind = ca.kind[s];
+        float other = ca.scalar[s];
+        if (kind == CH_ACC_IN || kind == CH_IN_ACC) {
+            other = next == 1 ? v1 : next == 2 ? v2 : v3;
+            next++;
+        }
+        acc = chain_exact_step(acc, other, kind, ca.op[s]);
+    }
+    return acc;
+}
+
 // A thread owns U output vectors: U consecutive rows of the blocked axis (U = kChainBlock) or a
 // single vector (U = 1). Operands that do not vary along the blocked axis are loaded once, and each
 // chain step is decoded once for all U*VEC lanes, which keeps the interpreter off the critical path
@@ -111,7 +178,7 @@ __device__ __forceinline__ void chain_step(float* acc, const float* other, int k
 constexpr int kChainBlock = 4;
 
 template <int VEC, int NIN, bool FULL, int U>
-__global__ void __launch_bounds__(kEwThreads) ew_chain_kernel(const ChainArgs<NIN> ca) {
+__global__ void __launch_bounds__(kEwThreads) ew_chain_kernel(const __grid_constant__ ChainArgs<NIN> ca) {
     using V = typename VecT<VEC>::type;
     const NdArgs<NIN>& a = ca.nd;
     const uint32_t item = blockIdx.x * (uint32_t)kEwThreads + threadIdx.x;
@@ -188,6 +255,25 @@ __global__ void __launch_bounds__(kEwThreads) ew_chain_kernel(const ChainArgs<NI
         }
         chain_step<FULL, U * VEC>(&acc[0][0], &other[0][0], kind, op);
     }
+    bool any_nan = false;
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int c = 0; c < VEC; c++) any_nan |= acc[u][c] != acc[u][c];
+    if (any_nan) {  // rare: replay those elements with the reference's NaN rules; operands are RE-READ (they are
+                    // still in L1/L2) so that the fast path does not have to keep them in registers
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int c = 0; c < VEC; c++)
+                if (acc[u][c] != acc[u][c] && (U == 1 || row0 + u < ca.blk_extent)) {
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int i = 0; i < NIN; i++)
+                        v[i] = __ldg(a.in[i] + off[i] + (U > 1 ? u * ca.blk_in[i] : 0) + ((VEC > 1 && a.inner_bcast[i]) ? 0 : c));
+                    acc[u][c] = chain_exact<NIN>(ca, v[0], v[1], v[2], v[3]);
+                }
+    }
 #pragma unroll
     for (int u = 0; u < U; u++) {
         if (U == 1 || row0 + u < ca.blk_extent) {
@@ -219,7 +305,7 @@ __device__ __forceinline__ void chain_apply_operand(float (&acc)[kChainRows][4],
 }
 
 template <int NIN, int INV>
-__global__ void __launch_bounds__(kEwThreads) ew_chain_blocked_kernel(const ChainArgs<NIN> ca) {
+__global__ void __launch_bounds__(kEwThreads) ew_chain_blocked_kernel(const __grid_constant__ ChainArgs<NIN> ca) {
     constexpr int U = kChainRows;
     const NdArgs<NIN>& a = ca.nd;
     const uint32_t item = blockIdx.x * (uint32_t)kEwThreads + threadIdx.x;
@@ -279,6 +365,24 @@ __global__ void __launch_bounds__(kEwThreads) ew_chain_blocked_kernel(const Chai
                 for (int c = 0; c < 4; c++) other[u][c] = ca.scalar[s];
             chain_step<false, U * 4>(&acc[0][0], &other[0][0], kind, op);
         }
+    }
+    bool any_nan = false;
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) any_nan |= acc[u][c] != acc[u][c];
+    if (any_nan) {  // rare: replay those elements with the reference's NaN rules (operands re-read, see ew_chain_kernel)
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (acc[u][c] != acc[u][c]) {
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int i = 0; i < NIN; i++)
+                        v[i] = __ldg(a.in[i] + off[i] + (((INV >> i) & 1) ? 0 : (long long)min((uint32_t)u, last_row) * ca.blk_in[i]) + c);
+                    acc[u][c] = chain_exact<NIN>(ca, v[0], v[1], v[2], v[3]);
+                }
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {

@@ -1,7 +1,11 @@
 // Runtime, storage, initialisers, host materialisation and metadata-only views.
 // Reference behaviour restated from arraylib/src/arraylib.c (line ranges cited per function);
 // the design (device pool, stream ordering, error channel) is new.
+#include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <map>
+#include <thread>
 #include <unordered_map>
 
 #include "al_internal.h"
@@ -358,6 +362,166 @@ bool fill_const(float* p, size_t n, float v) {
     return check_launch("fill_const");
 }
 
+
+// ---- pageable host memory <-> device through a pinned ring ---------------------------------------------------
+// The reference's from_numpy / to_numpy hand over ordinary (pageable) numpy buffers (core.py:340-363). A plain
+// cudaMemcpy of pageable memory is staged by the driver on ONE host thread (measured here: ~17 GB/s on the wire
+// against 55 GB/s for pinned memory). Large pageable transfers therefore go through the library's own ring of
+// pinned slots: helper threads copy between the caller's buffer and a slot while the DMA engine moves the
+// previous slot, uploads and downloads use separate rings and streams (PCIe is full duplex), and the API lock is
+// NOT held while bytes move, so one host thread can upload while another downloads.
+struct CopyPool {
+    struct Job {
+        char* dst;
+        const char* src;
+        size_t n;
+        std::atomic<int>* pending;
+    };
+    std::mutex m;
+    std::condition_variable cv;
+    std::deque<Job> q;
+    int helpers = 0;
+
+    void worker() {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return !q.empty(); });
+                j = q.front();
+                q.pop_front();
+            }
+            memcpy(j.dst, j.src, j.n);
+            j.pending->fetch_sub(1, std::memory_order_release);
+        }
+    }
+    void start() {
+        if (helpers) return;
+        unsigned hw = std::thread::hardware_concurrency();
+        const char* env = getenv("ARRAYLIB_COPY_THREADS");
+        helpers = env ? atoi(env) : (int)(hw / 3);
+        if (helpers < 1) helpers = 1;
+        if (helpers > 8) helpers = 8;
+        for (int i = 0; i < helpers; i++) std::thread([this] { worker(); }).detach();
+    }
+    // dst/src may be pageable or pinned; returns when every byte has been copied
+    void copy(char* dst, const char* src, size_t n) {
+        const size_t piece = (size_t)4 << 20;
+        size_t parts = (n + piece - 1) / piece;
+        if (parts > (size_t)helpers + 1) parts = (size_t)helpers + 1;
+        if (parts <= 1) {
+            memcpy(dst, src, n);
+            return;
+        }
+        const size_t each = ((n / parts) + 4095) & ~(size_t)4095;
+        std::atomic<int> pending{0};
+        size_t off = each;  // the caller's own share is [0, each)
+        {
+            std::lock_guard<std::mutex> lk(m);
+            while (off < n) {
+                const size_t len = std::min(each, n - off);
+                pending.fetch_add(1, std::memory_order_relaxed);
+                q.push_back({dst + off, src + off, len, &pending});
+                off += len;
+            }
+        }
+        cv.notify_all();
+        memcpy(dst, src, std::min(each, n));
+        while (pending.load(std::memory_order_acquire) > 0) std::this_thread::yield();
+    }
+};
+static CopyPool* g_copy_pool = nullptr;  // leaked on purpose: detached helpers may outlive static destruction
+
+constexpr int kRingSlots = 3;
+constexpr size_t kRingSlotBytes = (size_t)32 << 20;
+constexpr size_t kStagedMinBytes = (size_t)4 << 20;  // smaller transfers: the driver's own staging is as good
+struct PinnedRing {
+    std::mutex busy;  // one transfer per direction at a time
+    char* slot[kRingSlots] = {nullptr, nullptr, nullptr};
+    cudaEvent_t done[kRingSlots] = {nullptr, nullptr, nullptr};
+    bool ready() {
+        if (slot[0]) return true;
+        for (int i = 0; i < kRingSlots; i++) {
+            if (cudaHostAlloc((void**)&slot[i], kRingSlotBytes, cudaHostAllocDefault) != cudaSuccess ||
+                cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                for (int j = 0; j <= i; j++) {
+                    if (slot[j]) cudaFreeHost(slot[j]);
+                    slot[j] = nullptr;
+                }
+                return false;
+            }
+        }
+        return true;
+    }
+};
+static PinnedRing g_up_ring, g_down_ring;
+
+static bool is_pageable(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return attr.type == cudaMemoryTypeUnregistered;
+}
+
+static bool staging_enabled() { return g_rt.host_staging != 0; }
+
+// Upload `bytes` from pageable `src` to `dev` on the H2D stream. The caller has already made the H2D stream wait
+// for the compute stream. Returns once the SOURCE has been read completely (the last DMA may still be in flight).
+static bool staged_upload(float* dev, const char* src, size_t bytes) {
+    std::lock_guard<std::mutex> ring(g_up_ring.busy);
+    if (!g_up_ring.ready()) return set_error("MemoryError: cannot allocate the pinned upload ring"), false;
+    size_t off = 0;
+    for (int c = 0; off < bytes; c++) {
+        const int s = c % kRingSlots;
+        const size_t len = std::min(kRingSlotBytes, bytes - off);
+        if (c >= kRingSlots && !cuda_ok(cudaEventSynchronize(g_up_ring.done[s]), "cudaEventSynchronize(upload ring)")) return false;
+        g_copy_pool->copy(g_up_ring.slot[s], src + off, len);
+        if (!cuda_ok(cudaMemcpyAsync((char*)dev + off, g_up_ring.slot[s], len, cudaMemcpyHostToDevice, g_rt.h2d_stream),
+                     "cudaMemcpyAsync(H2D ring)") ||
+            !cuda_ok(cudaEventRecord(g_up_ring.done[s], g_rt.h2d_stream), "cudaEventRecord"))
+            return false;
+        off += len;
+    }
+    return true;
+}
+
+// Download `bytes` from `dev` into pageable `dst` on the D2H stream (which already waits for the compute stream).
+// Returns when `dst` is complete.
+static bool staged_download(char* dst, const float* dev, size_t bytes) {
+    std::lock_guard<std::mutex> ring(g_down_ring.busy);
+    if (!g_down_ring.ready()) return set_error("MemoryError: cannot allocate the pinned download ring"), false;
+    const size_t chunks = (bytes + kRingSlotBytes - 1) / kRingSlotBytes;
+    auto issue = [&](size_t c) {
+        const size_t off = c * kRingSlotBytes, len = std::min(kRingSlotBytes, bytes - off);
+        const int s = (int)(c % kRingSlots);
+        return cuda_ok(cudaMemcpyAsync(g_down_ring.slot[s], (const char*)dev + off, len, cudaMemcpyDeviceToHost, g_rt.d2h_stream),
+                       "cudaMemcpyAsync(D2H ring)") &&
+               cuda_ok(cudaEventRecord(g_down_ring.done[s], g_rt.d2h_stream), "cudaEventRecord");
+    };
+    for (size_t c = 0; c < chunks && c < (size_t)kRingSlots; c++)
+        if (!issue(c)) return false;
+    for (size_t c = 0; c < chunks; c++) {
+        const size_t off = c * kRingSlotBytes, len = std::min(kRingSlotBytes, bytes - off);
+        const int s = (int)(c % kRingSlots);
+        if (!cuda_ok(cudaEventSynchronize(g_down_ring.done[s]), "cudaEventSynchronize(download ring)")) return false;
+        g_copy_pool->copy(dst + off, g_down_ring.slot[s], len);
+        if (c + kRingSlots < chunks && !issue(c + kRingSlots)) return false;
+    }
+    return true;
+}
+
+static bool use_staging(const void* host, size_t bytes) {
+    if (!staging_enabled() || bytes < kStagedMinBytes || !is_pageable(host)) return false;
+    if (!g_copy_pool) {
+        g_copy_pool = new CopyPool();
+        g_copy_pool->start();
+    }
+    return true;
+}
+
 }  // namespace al
 
 using namespace al;
@@ -509,6 +673,7 @@ int al_set_tuning(const char* key, long value) {
     else if (k == "reduce_splits") g_rt.reduce_splits = value;
     else if (k == "reduce_sequential") g_rt.reduce_sequential = value;
     else if (k == "skip_zero_sign_fix") g_rt.skip_zero_sign_fix = value;
+    else if (k == "host_staging") g_rt.host_staging = value;
     else if (k == "reduce_loads_per_lane") g_rt.reduce_loads_per_lane = value;
     else if (k == "disable_window") g_rt.disable_window = value;
     else if (k == "window_shfl") g_rt.window_shfl = value;
@@ -649,17 +814,34 @@ NDArray* array_ones(const size_t* shape, size_t ndim) { return array_full(shape,
 
 // arraylib.c:282-288 -- `elems` is a host buffer; this is the H2D upload path.
 NDArray* array_fill(f32* elems, const size_t* shape, size_t ndim) {
-    AL_ENTER;
+    std::unique_lock<std::recursive_mutex> api(api_mutex());
+    clear_error();
     AL_REQUIRE(elems, "TypeError: array_fill got a NULL host buffer");
     NDArray* a = new_array(shape, ndim);
     if (!a) return nullptr;
-    bool ok = cuda_ok(cudaMemcpyAsync(a->ptr, elems, a->data->size * sizeof(float), cudaMemcpyHostToDevice,
-                                      g_rt.stream), "cudaMemcpyAsync(H2D)") &&
-              cuda_ok(cudaStreamSynchronize(g_rt.stream), "cudaStreamSynchronize");
+    const size_t bytes = a->data->size * sizeof(float);
+    bool ok;
+    if (use_staging(elems, bytes)) {
+        // the block may have just been released by work still queued on the compute stream
+        ok = cuda_ok(cudaEventRecord(g_rt.ev_copy, g_rt.stream), "cudaEventRecord") &&
+             cuda_ok(cudaStreamWaitEvent(g_rt.h2d_stream, g_rt.ev_copy, 0), "cudaStreamWaitEvent");
+        if (ok) {
+            api.unlock();  // other threads may launch kernels / download while the bytes move
+            ok = staged_upload(a->ptr, (const char*)elems, bytes);
+            api.lock();
+        }
+        if (ok) {  // like array_fill_async: the compute stream waits for the last DMA when the array is first used
+            cudaEvent_t landed = take_event();
+            ok = landed && cuda_ok(cudaEventRecord(landed, g_rt.h2d_stream), "cudaEventRecord");
+            if (ok) g_uploads[a->data] = landed;
+            else if (landed) g_event_pool.push_back(landed);
+        }
+    } else {
+        ok = cuda_ok(cudaMemcpyAsync(a->ptr, elems, bytes, cudaMemcpyHostToDevice, g_rt.stream), "cudaMemcpyAsync(H2D)") &&
+             cuda_ok(cudaStreamSynchronize(g_rt.stream), "cudaStreamSynchronize");
+    }
     if (!ok) {
-        std::string keep = g_err;
-        array_free(a);
-        g_err = keep;
+        release_array(a);
         return nullptr;
     }
     return a;
@@ -798,28 +980,34 @@ NDArray* array_linspace(f32 start, f32 end, f32 n) {
 
 // ---- host materialisation ------------------------------------------------------------------------
 int array_to_host(const NDArray* src, f32* dst) {
-    AL_ENTER;
+    std::unique_lock<std::recursive_mutex> api(api_mutex());
+    clear_error();
     if (!valid(src, "array_to_host")) return -1;
     if (!dst) {
         set_error("TypeError: array_to_host got a NULL destination");
         return -1;
     }
-    size_t n = count_of(src->lay->shape, src->lay->ndim);
-    const NDArray* from = src;
-    NDArray* tmp = nullptr;
-    if (!is_contiguous(src)) {
-        tmp = array_deep_copy(src);
-        if (!tmp) return -1;
-        from = tmp;
+    const size_t n = count_of(src->lay->shape, src->lay->ndim);
+    // a contiguous source is read in place (through an extra reference that keeps the block alive), anything else
+    // is gathered into a temporary first
+    NDArray* from = is_contiguous(src) ? new_view(src, src->lay->shape, src->lay->stride, src->lay->ndim, 0) : array_deep_copy(src);
+    if (!from) return -1;
+    bool ok;
+    if (use_staging(dst, n * sizeof(float))) {
+        ok = cuda_ok(cudaEventRecord(g_rt.ev_copy, g_rt.stream), "cudaEventRecord") &&
+             cuda_ok(cudaStreamWaitEvent(g_rt.d2h_stream, g_rt.ev_copy, 0), "cudaStreamWaitEvent");
+        if (ok) {
+            const float* dev = from->ptr;
+            api.unlock();
+            ok = staged_download((char*)dst, dev, n * sizeof(float));
+            api.lock();
+        }
+    } else {
+        ok = cuda_ok(cudaMemcpyAsync(dst, from->ptr, n * sizeof(float), cudaMemcpyDeviceToHost, g_rt.stream),
+                     "cudaMemcpyAsync(D2H)") &&
+             cuda_ok(cudaStreamSynchronize(g_rt.stream), "cudaStreamSynchronize");
     }
-    bool ok = cuda_ok(cudaMemcpyAsync(dst, from->ptr, n * sizeof(float), cudaMemcpyDeviceToHost, g_rt.stream),
-                      "cudaMemcpyAsync(D2H)") &&
-              cuda_ok(cudaStreamSynchronize(g_rt.stream), "cudaStreamSynchronize");
-    if (tmp) {
-        std::string keep = g_err;
-        array_free(tmp);
-        g_err = keep;
-    }
+    release_array(from);
     return ok ? 0 : -1;
 }
 
