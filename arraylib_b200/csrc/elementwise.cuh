@@ -22,6 +22,7 @@
 #pragma once
 #include "al_internal.h"
 #include "device_utils.cuh"
+#include "fast_pow.h"
 
 namespace al {
 
@@ -59,6 +60,14 @@ __device__ __forceinline__ float nan_like_sse(float res, float l, float r) {
     return nan_default_neg();
 }
 
+// (float)pow((double)l, (double)r) as the reference computes it (arraylib.c:17): fast_pow.h answers the elements
+// whose float rounding is certain (~40 FP64 operations), the rest go through the full double-precision pow.
+__device__ __forceinline__ float pow_like_reference(float l, float r) {
+    float fast;
+    if (fp_fast_pow(l, r, &fast)) return fast;
+    return (float)pow((double)l, (double)r);
+}
+
 // *_raw: the arithmetic alone (a NaN result is whatever the GPU makes of it: the canonical 0x7FFFFFFF);
 // *_apply: the same value, and when it is a NaN, the NaN the reference's build would have produced.
 template <int OP>
@@ -68,7 +77,7 @@ __device__ __forceinline__ float binop_raw(float l, float r) {
     else if constexpr (OP == AL_MUL) return __fmul_rn(l, r);
     else if constexpr (OP == AL_DIV) return __fdiv_rn(l, r);
     else if constexpr (OP == AL_MOD) return fmodf(l, r);  // fmod is exact, so f32 == round(f64)
-    else if constexpr (OP == AL_POW) return (float)pow((double)l, (double)r);
+    else if constexpr (OP == AL_POW) return pow_like_reference(l, r);
     // gcc's inline fmax / fmin: a NaN on the left yields the right operand (whatever it is), a NaN on the right
     // yields the left one, and on a +-0 tie the LEFT operand is returned
     else if constexpr (OP == AL_MAX) return (l >= r || (r != r && l == l)) ? l : r;

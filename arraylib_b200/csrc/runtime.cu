@@ -439,6 +439,7 @@ struct PinnedRing {
     std::mutex busy;  // one transfer per direction at a time
     char* slot[kRingSlots] = {nullptr, nullptr, nullptr};
     cudaEvent_t done[kRingSlots] = {nullptr, nullptr, nullptr};
+    bool in_flight[kRingSlots] = {false, false, false};  // a DMA out of this slot may still be running (uploads return early)
     bool ready() {
         if (slot[0]) return true;
         for (int i = 0; i < kRingSlots; i++) {
@@ -477,12 +478,15 @@ static bool staged_upload(float* dev, const char* src, size_t bytes) {
     for (int c = 0; off < bytes; c++) {
         const int s = c % kRingSlots;
         const size_t len = std::min(kRingSlotBytes, bytes - off);
-        if (c >= kRingSlots && !cuda_ok(cudaEventSynchronize(g_up_ring.done[s]), "cudaEventSynchronize(upload ring)")) return false;
+        // the slot may still be read by an earlier DMA -- of this transfer, or of the PREVIOUS one, which returned as
+        // soon as its source had been read
+        if (g_up_ring.in_flight[s] && !cuda_ok(cudaEventSynchronize(g_up_ring.done[s]), "cudaEventSynchronize(upload ring)")) return false;
         g_copy_pool->copy(g_up_ring.slot[s], src + off, len);
         if (!cuda_ok(cudaMemcpyAsync((char*)dev + off, g_up_ring.slot[s], len, cudaMemcpyHostToDevice, g_rt.h2d_stream),
                      "cudaMemcpyAsync(H2D ring)") ||
             !cuda_ok(cudaEventRecord(g_up_ring.done[s], g_rt.h2d_stream), "cudaEventRecord"))
             return false;
+        g_up_ring.in_flight[s] = true;
         off += len;
     }
     return true;

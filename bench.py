@@ -426,6 +426,8 @@ def run_gpu(args):
                  "gbs_vs_eager_algorithmic_bytes": round(eager_bytes / (fms * 1e-3) / 1e9, 1),
                  "gbs_vs_fused_algorithmic_bytes": round(fused_bytes / (fms * 1e-3) / 1e9, 1)}
     except Exception as exc:
+        if world > 1:  # a rank that skips the rest of a section would leave the other ranks' collectives unmatched
+            raise
         fused = {"error": repr(exc)}
 
     # ---- e2e: host buffers in, host buffers out, through the public API ----
@@ -520,6 +522,8 @@ def run_gpu(args):
                                 "note": "unmodified reference signatures from_numpy(x) / to_numpy(y) on pageable numpy arrays (to_numpy given a pageable `out` to avoid 24 GB of fresh allocations per step); downloads on one extra host thread"}
             del pageable, outs_pageable
         except Exception as exc:  # noqa: BLE001
+            if world > 1:
+                raise
             e2e["stock_api"] = {"error": repr(exc)}
         # what the host side of this box can move while ALL ranks copy at once (the ceiling of the e2e figure):
         # 1 GiB pinned each way per rank, one direction at a time and then both together
@@ -551,6 +555,8 @@ def run_gpu(args):
                                  "note": "aggregate over all ranks copying AT THE SAME TIME, 1 GiB pinned per rank and direction; the e2e step cannot move its bytes faster than this"}
             del pd, ph_in, ph_out
         except Exception as exc:  # noqa: BLE001
+            if world > 1:
+                raise
             e2e["pcie_probe"] = {"error": repr(exc)}
 
     # ---- the other scaling mode, briefly (N > 1 only) ----
