@@ -135,6 +135,7 @@ bool fill_const(float* p, size_t n, float v);
 // Every extern "C" entry point serialises on one lock (ctypes drops the GIL around calls) and
 // starts with a clean error slot.
 std::recursive_mutex& api_mutex();
+void bind_thread();  // makes the library's device current on the calling host thread (new threads start on device 0)
 const std::string& last_error_string();
 void restore_error(const std::string& s);
 
@@ -142,4 +143,5 @@ void restore_error(const std::string& s);
 
 #define AL_ENTER                                                     \
     std::lock_guard<std::recursive_mutex> _guard(::al::api_mutex()); \
+    ::al::bind_thread();                                             \
     ::al::clear_error()

@@ -70,7 +70,7 @@ static bool nccl_ok(ncclResult_t r, const char* what) {
 
 // ---- peer-memory windows (see peer.cuh for the protocol) -------------------------------------------------
 constexpr size_t kFlagBytes = 4096;            // 2 x [kMaxPeers] u32 arrival counters, padded
-constexpr long long kPeerTimeoutNs = 60ll * 1000 * 1000 * 1000;  // a rank may legitimately lag (host work between collectives)
+constexpr long long kPeerTimeoutNs = 180ll * 1000 * 1000 * 1000;  // a rank may legitimately lag (host work between collectives)
 
 struct PeerWindows {
     bool tried = false, ok = false;
@@ -445,7 +445,10 @@ int al_comm_allreduce(NDArray* a, int redop) {
     if (peer_error_raised()) return -1;
     size_t n = count_of(a->lay->shape, a->lay->ndim);
     PeerMap map;
-    if (peer_begin(n, &map)) {  // same windows as al_comm_reduce: push, rank-ordered combine, collect (in place)
+    // Small messages are barriers and host scalars (dist.barrier, allreduce_scalar): ranks may legitimately arrive
+    // minutes apart there (one of them is still on the host), which the bounded wait of the peer kernels would report
+    // as a failure. They go through NCCL, which simply waits.
+    if (n * sizeof(float) >= (64u << 10) && peer_begin(n, &map)) {  // same windows as al_comm_reduce: push, rank-ordered combine, collect (in place)
         const float ident[AL_REDOP_COUNT] = {0.0f, -INFINITY, INFINITY, 1.0f};
         return peer_push(a->ptr, n, map) && peer_finish(redop, a->ptr, n, ident[redop], false) ? 0 : -1;
     }

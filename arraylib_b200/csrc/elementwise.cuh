@@ -129,6 +129,10 @@ __device__ __forceinline__ float ufunc_raw(float v) {
     else if constexpr (OP == AL_CEIL) return ceilf(v);
     else if constexpr (OP == AL_FLOOR) return floorf(v);
     else {
+        if constexpr (OP == AL_LOG) {  // fast_pow.h: accepted when the float rounding of the result is certain
+            float fast;
+            if (fp_fast_log(v, &fast)) return fast;
+        }
         double x = (double)v;
         if constexpr (OP == AL_EXP) x = exp(x);
         else if constexpr (OP == AL_LOG) x = log(x);

@@ -32,14 +32,15 @@ FP_HD uint64_t fp_bits(double d) { uint64_t u; memcpy(&u, &d, 8); return u; }
 FP_HD double fp_from_bits(uint64_t u) { double d; memcpy(&d, &u, 8); return d; }
 
 
-// log2 of a positive normal double that came from a float. Returns L with abs error <= ~2^-49 * max(0.5, |L|).
-FP_HD double fp_log2(double x) {
+// Natural log of the mantissa of a positive normal double that came from a float: x = 2^e * m with m in
+// [sqrt(1/2), sqrt(2)); returns log(m) with a relative error of a few 2^-53 and stores e.
+FP_HD double fp_log_mantissa(double x, int* e_out) {
     uint64_t ix = fp_bits(x);
     int e = (int)(ix >> 52) - 1023;
     uint64_t mant = ix & 0x000fffffffffffffull;
-    // m in [sqrt(1/2), sqrt(2))
     if (mant > 0x6a09e667f3bcdull) { e += 1; ix = mant | 0x3fe0000000000000ull; }
     else ix = mant | 0x3ff0000000000000ull;
+    *e_out = e;
     const double m = fp_from_bits(ix);
     const double num = m - 1.0, den = m + 1.0;  // both exact (m has <= 24 significant bits here)
     const double q0 = (double)FP_RCP32((float)den);
@@ -59,11 +60,38 @@ FP_HD double fp_log2(double x) {
     p = fma(p, z, 1.0 / 5.0);
     p = fma(p, z, 1.0 / 3.0);
     const double two_s = s + s;
-    const double lm = fma(two_s * z, p, two_s);  // log(m)
-    // log2(m) = lm / ln2, with 1/ln2 split hi + lo
-    const double inv_hi = 1.4426950408889634, inv_lo = 2.0355273740931033e-17;
-    const double l2 = fma(lm, inv_lo, lm * inv_hi);
-    return (double)e + l2;
+    return fma(two_s * z, p, two_s);
+}
+
+// log2 of a positive normal double that came from a float. Abs error <= ~2^-52 * max(0.5, |L|).
+FP_HD double fp_log2(double x) {
+    int e;
+    const double lm = fp_log_mantissa(x, &e);
+    const double inv_hi = 1.4426950408889634, inv_lo = 2.0355273740931033e-17;  // 1/ln2 = hi + lo
+    return (double)e + fma(lm, inv_lo, lm * inv_hi);
+}
+
+// (float)log((double)x) when that rounding is certain (same acceptance rule as fp_fast_pow), else 0.
+FP_HD int fp_fast_log(float xf, float* out) {
+    uint32_t xb; memcpy(&xb, &xf, 4);
+    if (xb == 0x3f800000u) { *out = 0.0f; return 1; }
+    if (xb < 0x00800000u || xb >= 0x7f800000u) {
+        if ((xb & 0x7fffffffu) == 0) { *out = -INFINITY; return 1; }                // log(+-0) = -inf
+        if (xb == 0x7f800000u) { *out = INFINITY; return 1; }
+        if ((xb >> 31) && (xb & 0x7fffffffu) <= 0x7f800000u) { *out = NAN; return 1; }  // negative (incl. -inf): domain error
+        return 0;  // subnormal or NaN: slow path
+    }
+    int e;
+    const double lm = fp_log_mantissa((double)xf, &e);
+    const double ln2_hi = 0.6931471805599453, ln2_lo = 2.3190468138462996e-17;
+    const double r = fma((double)e, ln2_hi, fma((double)e, ln2_lo, lm));
+    const uint32_t low = (uint32_t)(fp_bits(r) & 0x1fffffffu);
+    const uint32_t d = low > 0x10000000u ? low - 0x10000000u : 0x10000000u - low;
+    if (d < (1u << 15)) return 0;
+    const double ar = fabs(r);
+    if (!(ar > 1.2e-38)) return 0;
+    *out = (float)r;
+    return 1;
 }
 
 // 2^t for |t| < 1000, relative error ~2^-50
@@ -103,7 +131,10 @@ FP_HD int fp_fast_pow(float xf, float yf, float* out) {
     int negate = 0;
     if (xb >> 31) {  // negative base: only integer exponents have a real result
         const float ay = fabsf(yf);
-        if (ay != truncf(ay)) return 0;
+        if (ay != truncf(ay)) {  // domain error: a NaN (the caller gives it the reference's sign, elementwise.cuh)
+            *out = NAN;
+            return 1;
+        }
         negate = ay < 16777216.0f && (((int)ay) & 1);
     }
     const double x = (double)fabsf(xf), y = (double)yf;

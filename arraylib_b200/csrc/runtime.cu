@@ -17,6 +17,16 @@ static thread_local std::string g_err;
 static std::recursive_mutex g_api_mutex;
 
 Runtime& rt() { return g_rt; }
+// A host thread that enters the library for the first time has CUDA device 0 current, whatever device the process
+// was bound to: events created and recorded from such a thread then belong to the wrong device ("invalid resource
+// handle" on ranks > 0 as soon as a second Python thread calls to_numpy). Every entry point re-binds its thread.
+static thread_local int t_bound_device = -1;
+void bind_thread() {
+    if (g_rt.device >= 0 && t_bound_device != g_rt.device) {
+        cudaSetDevice(g_rt.device);
+        t_bound_device = g_rt.device;
+    }
+}
 std::recursive_mutex& api_mutex() { return g_api_mutex; }
 const std::string& last_error_string() { return g_err; }
 void restore_error(const std::string& s) { g_err = s; }
@@ -558,6 +568,7 @@ int al_init(int device) {
     if (!cuda_ok(cudaEventCreate(&g_rt.ev_start), "cudaEventCreate")) return -1;
     if (!cuda_ok(cudaEventCreate(&g_rt.ev_stop), "cudaEventCreate")) return -1;
     g_rt.device = device;
+    t_bound_device = device;
     // ARRAYLIB_TUNING="key=value,key=value": the al_set_tuning knobs from the environment
     if (const char* env = getenv("ARRAYLIB_TUNING")) {
         std::string spec(env);
@@ -819,6 +830,7 @@ NDArray* array_ones(const size_t* shape, size_t ndim) { return array_full(shape,
 // arraylib.c:282-288 -- `elems` is a host buffer; this is the H2D upload path.
 NDArray* array_fill(f32* elems, const size_t* shape, size_t ndim) {
     std::unique_lock<std::recursive_mutex> api(api_mutex());
+    bind_thread();
     clear_error();
     AL_REQUIRE(elems, "TypeError: array_fill got a NULL host buffer");
     NDArray* a = new_array(shape, ndim);
@@ -985,6 +997,7 @@ NDArray* array_linspace(f32 start, f32 end, f32 n) {
 // ---- host materialisation ------------------------------------------------------------------------
 int array_to_host(const NDArray* src, f32* dst) {
     std::unique_lock<std::recursive_mutex> api(api_mutex());
+    bind_thread();
     clear_error();
     if (!valid(src, "array_to_host")) return -1;
     if (!dst) {

@@ -116,8 +116,9 @@ def test_c4_reduce_sum_normal_data_within_the_stated_tolerance(al, orc, ref, rng
         assert (np.abs(got - serial) <= tol).all(), f"dims {dims}: |gpu - ref| exceeds 2 n eps sum|x|"
         assert (np.abs(got - exact) <= np.abs(serial - exact) + 2.0 ** -22 * np.abs(exact) + tol / 2).all()
         # what the tree actually achieves, in units of eps * sum|x| (a pairwise tree is O(log n), the serial loop O(n))
-        gpu_err = float((np.abs(got - exact) / (eps * sabs)).max())
-        ref_err = float((np.abs(serial - exact) / (eps * sabs)).max())
+        scale = np.where(sabs > 0, eps * sabs, 1.0)  # (an all-zero reduced set has no error to measure)
+        gpu_err = float((np.abs(got - exact) / scale).max())
+        ref_err = float((np.abs(serial - exact) / scale).max())
         print(f"C4 reduce_sum dims={dims} n={n}: max |err| / (eps sum|x|): gpu {gpu_err:.3f}, serial reference {ref_err:.3f}")
         assert gpu_err <= 2 * np.log2(n) + 2
 
