@@ -381,3 +381,34 @@ def test_nan_sign_and_payload_follow_the_reference_unary(al, orc):
             want = orc.unary(op, s)
         exact = op in ("neg", "abs", "sqrt", "ceil", "floor")
         _assert_nan_strict(al.to_numpy(getattr(al, op)(al.from_numpy(s))), want, op, ulp=0 if exact else 1)
+
+
+def test_pow_and_log_fast_paths_match_glibc_bit_for_bit(al, orc, rng):
+    """csrc/fast_pow.h answers most pow / log elements with ~40 FP64 operations and hands the rest to the full
+    double-precision routine. Against the oracle (glibc pow / log in double, rounded once: arraylib.c:17, 35) on 2^21
+    operands per mix: positive bases with real exponents, negative bases with integer and non-integer exponents,
+    squares, values next to 1, huge and tiny results, every special value."""
+    n = 1 << 21
+    def near_one(k):
+        return (np.float32(1.0) + (rng.integers(-1024, 1025, size=k).astype(np.float32) * np.float32(2.0 ** -23))).astype(np.float32)
+    any_bits = rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32).view(np.float32)
+    mixes = {
+        "pos^real": (rng.uniform(0.5, 4.0, n).astype(np.float32), rng.uniform(-4.0, 4.0, n).astype(np.float32)),
+        "normal^normal": (rng.standard_normal(n).astype(np.float32) * 3, rng.standard_normal(n).astype(np.float32) * 3),
+        "any^smallint": (rng.uniform(-30.0, 30.0, n).astype(np.float32), rng.integers(-20, 21, size=n).astype(np.float32)),
+        "near1^big": (near_one(n), rng.uniform(-1e6, 1e6, n).astype(np.float32)),
+        "big^big": (rng.uniform(0.0, 1e6, n).astype(np.float32), rng.uniform(-40.0, 40.0, n).astype(np.float32)),
+        "bits^bits": (any_bits, np.roll(any_bits, 12345)),
+        "x^2": (rng.standard_normal(n).astype(np.float32) * np.float32(1e3), np.full(n, 2.0, np.float32)),
+    }
+    with np.errstate(all="ignore"):
+        for name, (x, y) in mixes.items():
+            got = al.to_numpy(al.pow(al.from_numpy(x), al.from_numpy(y)))
+            assert_bit_equal(got, orc.binary("pow", x, y), f"pow {name}")
+        got = al.to_numpy(al.from_numpy(mixes["x^2"][0]) ** 2.0)  # scalar exponent
+        assert_bit_equal(got, orc.binary("pow", mixes["x^2"][0], 2.0), "pow scalar 2")
+        got = al.to_numpy(al.from_numpy(mixes["pos^real"][0]) ** 0.5)
+        assert_bit_equal(got, orc.binary("pow", mixes["pos^real"][0], 0.5), "pow scalar 0.5")
+        for name, x in {"pos": rng.uniform(1e-30, 1e30, n).astype(np.float32), "near1": near_one(n), "normal": rng.standard_normal(n).astype(np.float32),
+                        "bits": any_bits, "small": rng.uniform(0.0, 2.0, n).astype(np.float32)}.items():
+            assert_bit_equal(al.to_numpy(al.log(al.from_numpy(x))), orc.unary("log", x), f"log {name}")
