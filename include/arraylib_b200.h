@@ -15,9 +15,12 @@
  *   - Host callbacks cannot run on the device: array_op / array_reduce (which take C function
  *     pointers in the reference) fail with NotImplementedError. Their replacements are
  *     array_op_named / array_reduce_named, which take an entry of the ufunc tables below.
- *   - Numerics: elementwise results are bit-identical to the reference's x86-64 / glibc build, NaN sign and
- *     payload included; reduce_sum sums in a tree (stated tolerance), and the fused
- *     chain / tape extensions return the GPU's canonical NaN where the eager path returns the x86 one.
+ *   - Numerics: elementwise results -- eager or fused chain -- are bit-identical to the reference's x86-64 / glibc
+ *     build, NaN sign and payload included; reduce_max / reduce_min are bit-identical,
+ *     the sign of a zero result included; reduce_sum sums in a tree (stated tolerance); the FP64 tape extension
+ *     returns the GPU's canonical NaN.
+ *   - array_fill / array_to_host accept ordinary pageable host memory, like the reference; transfers of 4 MiB and
+ *     more are staged through a pinned ring inside the library and do not hold the API lock while bytes move.
  *
  * Reference citations are relative to /root/reference.
  */
