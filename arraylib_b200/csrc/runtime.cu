@@ -407,11 +407,16 @@ struct CopyPool {
     }
     void start() {
         if (helpers) return;
+        // half of this rank's share of the host cores (the ranks of one box split them): 8 on a 16-core single-GPU
+        // box, 2 per rank with 8 ranks on 32 cores
         unsigned hw = std::thread::hardware_concurrency();
+        const char* lw = getenv("LOCAL_WORLD_SIZE");
+        int ranks = lw ? atoi(lw) : 1;
+        if (ranks < 1) ranks = 1;
         const char* env = getenv("ARRAYLIB_COPY_THREADS");
-        helpers = env ? atoi(env) : (int)(hw / 3);
+        helpers = env ? atoi(env) : (int)(hw / (2 * (unsigned)ranks));
         if (helpers < 1) helpers = 1;
-        if (helpers > 8) helpers = 8;
+        if (helpers > 12) helpers = 12;
         for (int i = 0; i < helpers; i++) std::thread([this] { worker(); }).detach();
     }
     // dst/src may be pageable or pinned; returns when every byte has been copied

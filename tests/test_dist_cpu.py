@@ -218,3 +218,17 @@ def test_shim_selects_the_spmd_front_end_only_on_request(monkeypatch):
     assert importlib.reload(arraylib).NDArray.__module__ == "arraylib_b200.core"
     monkeypatch.delenv("WORLD_SIZE")
     importlib.reload(arraylib)
+
+
+def test_scatter_refuses_fewer_rows_than_ranks_on_every_rank(monkeypatch):
+    """with fewer leading rows than ranks some ranks would own an empty block and fail alone while the
+    others walked into a collective. The check runs before anything is uploaded, with the same outcome on every rank."""
+    monkeypatch.setitem(dist._state, "world", 4)
+    for rank in range(4):
+        monkeypatch.setitem(dist._state, "rank", rank)
+        with pytest.raises(ValueError, match="smaller than the world size"):
+            dist.scatter_from_numpy(np.zeros((3, 8), np.float32))
+        with pytest.raises(ValueError, match="smaller than the world size"):
+            dist.ShardedArray.scatter(np.zeros((1, 2, 8), np.float32))
+        with pytest.raises(ValueError, match="smaller than the world size"):
+            dist.window_shard_from_numpy(np.zeros((66,), np.float32), 64)
