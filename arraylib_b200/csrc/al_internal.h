@@ -50,6 +50,9 @@ struct Runtime {
     long stream_tma = 0;       // 1: contiguous add/mul through the cp.async.bulk + mbarrier pipeline (experiment)
     long interleave = 1;       // 0: short-axis transposes always use the rectangular tile kernel
     long outer_tile = 1;       // 0: do not use the register-tiled outer-broadcast kernel
+    long period_plan = 1;      // 0: short-inner-axis layouts stay on ew_run (no period tables)
+    long heavy_stream = 1;     // persistent prefetching kernel for contiguous streams: 0 never, 1 pow, 2 pow and the FP64 ufuncs
+    long heavy_ctas_per_sm = 0;  // persistent CTAs per SM of ew_heavy_stream_kernel (0 = as many as are resident)
     long host_staging = 1;     // 0: pageable from_numpy / to_numpy use plain cudaMemcpy instead of the library's pinned ring + copy threads
     long peer_collective = 1;  // 0: cross-GPU reductions go through ncclAllReduce instead of the peer-memory windows
 };

@@ -20,9 +20,12 @@
 //   ew_run           anything else: 4 consecutive outputs per thread, linear index resolved once and
 //                    stepped with carries; ew_nd<VEC=1> for flat (1-D) streams.
 #pragma once
+#include <type_traits>
+
 #include "al_internal.h"
 #include "device_utils.cuh"
 #include "fast_pow.h"
+#include "fast_ufunc.h"
 
 namespace al {
 
@@ -129,10 +132,26 @@ __device__ __forceinline__ float ufunc_raw(float v) {
     else if constexpr (OP == AL_CEIL) return ceilf(v);
     else if constexpr (OP == AL_FLOOR) return floorf(v);
     else {
-        if constexpr (OP == AL_LOG) {  // fast_pow.h: accepted when the float rounding of the result is certain
-            float fast;
-            if (fp_fast_log(v, &fast)) return fast;
-        }
+        // fast_ufunc.h: short double-precision kernels, accepted when the float rounding of the result is certain
+        // (bit-identical to the reference's glibc result, validated over all 2^32 operands on the CPU); the other
+        // ~0.012 % of the elements and out-of-range operands run CUDA's full double-precision routine below
+        float fast = 0.0f;
+        bool have = false;
+        if constexpr (OP == AL_EXP) have = fu_fast_exp(v, &fast);
+        else if constexpr (OP == AL_LOG) have = fu_fast_log(v, &fast);
+        else if constexpr (OP == AL_SIN) have = fu_fast_sin(v, &fast);
+        else if constexpr (OP == AL_COS) have = fu_fast_cos(v, &fast);
+        else if constexpr (OP == AL_TAN) have = fu_fast_tan(v, &fast);
+        else if constexpr (OP == AL_ASIN) have = fu_fast_asin(v, &fast);
+        else if constexpr (OP == AL_ACOS) have = fu_fast_acos(v, &fast);
+        else if constexpr (OP == AL_ATAN) have = fu_fast_atan(v, &fast);
+        else if constexpr (OP == AL_SINH) have = fu_fast_sinh(v, &fast);
+        else if constexpr (OP == AL_COSH) have = fu_fast_cosh(v, &fast);
+        else if constexpr (OP == AL_TANH) have = fu_fast_tanh(v, &fast);
+        else if constexpr (OP == AL_ASINH) have = fu_fast_asinh(v, &fast);
+        else if constexpr (OP == AL_ACOSH) have = fu_fast_acosh(v, &fast);
+        else if constexpr (OP == AL_ATANH) have = fu_fast_atanh(v, &fast);
+        if (have) return fast;
         double x = (double)v;
         if constexpr (OP == AL_EXP) x = exp(x);
         else if constexpr (OP == AL_LOG) x = log(x);
@@ -165,42 +184,58 @@ __device__ __forceinline__ float ufunc_apply(float v) {
 template <int OP>
 struct BinF {
     static constexpr int NIN = 2;
+    static constexpr int kHeavy = OP == AL_POW ? 1 : 0;  // FP64 work per element: contiguous streams take ew_heavy_stream_kernel (level: see heavy_stream)
     __device__ __forceinline__ float operator()(const float* v) const { return binop_apply<OP>(v[0], v[1]); }
+    __device__ __forceinline__ float raw(const float* v) const { return binop_raw<OP>(v[0], v[1]); }  // the value; a NaN not yet the reference's
 };
 template <int OP>
 struct ScalarF {
     static constexpr int NIN = 1;
+    static constexpr int kHeavy = OP == AL_POW ? 1 : 0;
     float s;
     __device__ __forceinline__ float operator()(const float* v) const { return binop_apply<OP>(v[0], s); }
+    __device__ __forceinline__ float raw(const float* v) const { return binop_raw<OP>(v[0], s); }
 };
 template <int OP>
 struct UnaryF {
     static constexpr int NIN = 1;
+    static constexpr int kHeavy = OP >= AL_EXP && OP <= AL_ATANH ? 2 : 0;
     __device__ __forceinline__ float operator()(const float* v) const { return ufunc_apply<OP>(v[0]); }
+    __device__ __forceinline__ float raw(const float* v) const { return ufunc_apply<OP>(v[0]); }  // (neg / abs must keep NaN payloads: no shortcut)
 };
+template <typename F, typename = void>
+struct is_heavy : std::false_type {};
+template <typename F>
+struct is_heavy<F, std::void_t<decltype(F::kHeavy)>> : std::bool_constant<(F::kHeavy > 0)> {};
+
 struct CopyF {
     static constexpr int NIN = 1;
     __device__ __forceinline__ float operator()(const float* v) const { return v[0]; }
+    __device__ __forceinline__ float raw(const float* v) const { return v[0]; }
 };
 // where: C truthiness of an f32, i.e. (x != 0): NaN selects lhs, +-0 selects rhs (arraylib.c:788)
 struct WhereAAA {
     static constexpr int NIN = 3;
     __device__ __forceinline__ float operator()(const float* v) const { return v[0] != 0.0f ? v[1] : v[2]; }
+    __device__ __forceinline__ float raw(const float* v) const { return (*this)(v); }
 };
 struct WhereAAS {
     static constexpr int NIN = 2;
     float r;
     __device__ __forceinline__ float operator()(const float* v) const { return v[0] != 0.0f ? v[1] : r; }
+    __device__ __forceinline__ float raw(const float* v) const { return (*this)(v); }
 };
 struct WhereASA {
     static constexpr int NIN = 2;
     float l;
     __device__ __forceinline__ float operator()(const float* v) const { return v[0] != 0.0f ? l : v[1]; }
+    __device__ __forceinline__ float raw(const float* v) const { return (*this)(v); }
 };
 struct WhereASS {
     static constexpr int NIN = 1;
     float l, r;
     __device__ __forceinline__ float operator()(const float* v) const { return v[0] != 0.0f ? l : r; }
+    __device__ __forceinline__ float raw(const float* v) const { return (*this)(v); }
 };
 
 // ---- N-d kernel --------------------------------------------------------------------------------
@@ -338,6 +373,65 @@ __global__ void __launch_bounds__(kEwThreads) ew_nd_kernel(const NdArgs<F::NIN> 
             }
             store_vec<VEC>(a.out + (size_t)item * VEC, r, a.stream_store);
         }
+    }
+}
+
+// ---- contiguous streams under a compute-heavy functor (the FP64 ufuncs, pow) ----------------------------------------
+// ew_nd issues all of a thread's loads, waits, computes, stores and exits. With 40-130 instructions per element the
+// compute phase is as long as the memory latency, and at 48-64 registers only 8 warps per scheduler are resident, so
+// DRAM sat idle while the warps computed: exp ran at 4.5 TB/s with the FP64 pipe and the issue slots both ~60 % busy.
+// Here the CTAs are persistent and every thread keeps the NEXT batch's 128-bit loads in flight while it computes the
+// current one (register double buffer), so memory time and compute time overlap instead of adding up.
+constexpr int kHeavyUnroll = 2;
+
+template <typename F>
+__global__ void __launch_bounds__(kEwThreads) ew_heavy_stream_kernel(float* __restrict__ out, const float* __restrict__ in0,
+                                                                     const float* __restrict__ in1, uint32_t n4, const F f,
+                                                                     int stream_store) {
+    constexpr int NIN = F::NIN, U = kHeavyUnroll;
+    static_assert(NIN <= 2, "one or two streamed operands");
+    const uint32_t step = gridDim.x * (uint32_t)(kEwThreads * U);
+    uint32_t i = blockIdx.x * (uint32_t)(kEwThreads * U) + threadIdx.x;
+    float4 cur[U][NIN], nxt[U][NIN];
+    auto fetch = [&](float4 (*dst)[NIN], uint32_t at) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t j = at + u * kEwThreads;
+            if (j < n4) {
+                dst[u][0] = __ldcs(reinterpret_cast<const float4*>(in0) + j);
+                if constexpr (NIN == 2) dst[u][1] = __ldcs(reinterpret_cast<const float4*>(in1) + j);
+            }
+        }
+    };
+    fetch(cur, i);
+    for (; i < n4; i += step) {
+        fetch(nxt, i + step);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t j = i + u * kEwThreads;
+            if (j < n4) {
+                float4 r;
+                float x[NIN];
+#pragma unroll
+                for (int k = 0; k < NIN; k++) x[k] = cur[u][k].x;
+                r.x = f(x);
+#pragma unroll
+                for (int k = 0; k < NIN; k++) x[k] = cur[u][k].y;
+                r.y = f(x);
+#pragma unroll
+                for (int k = 0; k < NIN; k++) x[k] = cur[u][k].z;
+                r.z = f(x);
+#pragma unroll
+                for (int k = 0; k < NIN; k++) x[k] = cur[u][k].w;
+                r.w = f(x);
+                if (stream_store) __stcs(reinterpret_cast<float4*>(out) + j, r);
+                else reinterpret_cast<float4*>(out)[j] = r;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int k = 0; k < NIN; k++) cur[u][k] = nxt[u][k];
     }
 }
 
@@ -493,6 +587,170 @@ __global__ void __launch_bounds__(kEwThreads) ew_run_kernel(const NdArgs<F::NIN>
         for (int j = 0; j < kRun; j++)
             if (e0 + j < a.n_items) dst[j] = r[j];
     }
+}
+
+// ---- period kernel: short inner axes under operands that fit none of ew_run's cheap modes ---------------------------
+// "[4096,1,5,3] + [1,2048,1,3]", "[N,1,7] + [1,9,7]": with inner extents of 3..7 the four outputs of an ew_run thread
+// span up to three rows and every row costs a divmod chain per operand (1.2-3 TB/s, issue-bound). Here the innermost
+// axes -- whole axes while their product stays <= kPerMax, then the largest divisor of the next axis that still fits --
+// form a PERIOD of P outputs. Each CTA tabulates, once, what every operand does inside a period: its VALUES when the
+// operand does not depend on anything above the period (kind 1: the broadcast operand's period staged in shared
+// memory), else its element OFFSETS (kind 2). A thread then owns 4 consecutive outputs, needs one division (e / P) and
+// one chain over the OUTER axes only, and reads its 4 table entries with one 128-bit shared load: the table is kept in
+// four copies shifted by 0..3 entries (and extended by 3 entries past the wrap), so the load is aligned for every
+// phase of e mod P. Only threads whose 4 outputs cross into the next period resolve a second outer chain.
+constexpr int kPerMax = 512;
+
+template <int NIN>
+struct PerArgs {
+    float* out;
+    const float* in[NIN];
+    uint32_t n_items, period;
+    FastDiv period_div;
+    int n_inner, n_outer;
+    uint32_t in_ext[kMaxDims], out_ext[kMaxDims];
+    FastDiv in_div[kMaxDims], out_div[kMaxDims];
+    uint32_t in_stride[NIN][kMaxDims], out_stride[NIN][kMaxDims];  // element strides; every operand spans < 2^32 elements
+    unsigned char kind[NIN];  // 0: laid out like the output (128-bit loads), 1: values staged, 2: offsets staged
+    unsigned char stream_store, out_aligned;
+};
+
+template <int NIN>
+__device__ __forceinline__ void per_outer_offsets(const PerArgs<NIN>& a, uint32_t q, uint32_t* off) {
+#pragma unroll
+    for (int i = 0; i < NIN; i++) off[i] = 0;
+    uint32_t rem = q;
+#pragma unroll
+    for (int d = 0; d < kMaxDims; d++) {
+        if (d >= a.n_outer) break;
+        uint32_t idx;
+        if (d == a.n_outer - 1) {
+            idx = rem;
+        } else {
+            const uint32_t qq = fdiv(rem, a.out_div[d]);
+            idx = rem - qq * a.out_ext[d];
+            rem = qq;
+        }
+#pragma unroll
+        for (int i = 0; i < NIN; i++) off[i] += idx * a.out_stride[i][d];
+    }
+}
+
+// One group of 4 consecutive outputs starting at e0. GUARD: the ragged last group (per-element bounds checks);
+// K0..K2: operand kinds known at compile time (3 = read a.kind[i]), which removes every per-operand branch from the loop.
+template <typename F, int K0, int K1, int K2, bool GUARD>
+__device__ __forceinline__ void per_group(const PerArgs<F::NIN>& a, const F& f, const uint32_t (*tbl)[4][kPerMax + 4], uint32_t e0) {
+    constexpr int NIN = F::NIN;
+    constexpr int KS[3] = {K0, K1, K2};
+    const uint32_t P = a.period;
+    const uint32_t q = fdiv(e0, a.period_div), r = e0 - q * P;
+    const uint32_t s = r & 3u, j = r - s;
+    uint32_t o0[NIN], o1[NIN];
+    if (a.n_outer == 1) {  // the usual case: one axis above the period
+#pragma unroll
+        for (int i = 0; i < NIN; i++) o0[i] = q * a.out_stride[i][0], o1[i] = o0[i] + a.out_stride[i][0];
+    } else {
+        per_outer_offsets<NIN>(a, q, o0);
+        if (r + 3 >= P) {
+            per_outer_offsets<NIN>(a, q + 1, o1);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NIN; i++) o1[i] = o0[i];
+        }
+    }
+    const uint32_t wrap = P - r;  // elements c >= wrap belong to the next period
+    float v[4][NIN];
+#pragma unroll
+    for (int i = 0; i < NIN; i++) {
+        const int kind = KS[i] == 3 ? (int)a.kind[i] : KS[i];
+        if (kind == 0) {
+            if (!GUARD) {
+                const float4 d = __ldcs(reinterpret_cast<const float4*>(a.in[i] + e0));
+                v[0][i] = d.x, v[1][i] = d.y, v[2][i] = d.z, v[3][i] = d.w;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    if (e0 + c < a.n_items) v[c][i] = __ldg(a.in[i] + e0 + c);
+            }
+        } else {
+            const uint4 t = *reinterpret_cast<const uint4*>(&tbl[i][s][j]);
+            const uint32_t tv[4] = {t.x, t.y, t.z, t.w};
+            if (kind == 1) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) v[c][i] = __uint_as_float(tv[c]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    if (!GUARD || e0 + c < a.n_items) v[c][i] = __ldg(a.in[i] + (tv[c] + ((uint32_t)c >= wrap ? o1[i] : o0[i])));
+            }
+        }
+    }
+    float* dst = a.out + e0;
+    if (!GUARD) {
+        // the bare arithmetic first; one NaN test for the four results (a NaN survives the sum; inf - inf only costs a
+        // detour), and only then the functor's own NaN rules (sign and payload of the reference's build)
+        float y[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) y[c] = f.raw(v[c]);
+        const float probe = (y[0] + y[1]) + (y[2] + y[3]);
+        if (probe != probe) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) y[c] = f(v[c]);
+        }
+        if (a.out_aligned) {
+            const float4 r4 = make_float4(y[0], y[1], y[2], y[3]);
+            if (a.stream_store) __stcs(reinterpret_cast<float4*>(dst), r4);
+            else *reinterpret_cast<float4*>(dst) = r4;
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; c++) dst[c] = y[c];
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            if (e0 + c < a.n_items) dst[c] = f(v[c]);
+    }
+}
+
+template <typename F, int K0, int K1, int K2>
+__global__ void __launch_bounds__(kEwThreads) ew_period_kernel(const PerArgs<F::NIN> a, const F f) {
+    constexpr int NIN = F::NIN;
+    constexpr int KS[3] = {K0, K1, K2};
+    __shared__ __align__(16) uint32_t tbl[NIN][4][kPerMax + 4];
+    const uint32_t P = a.period;
+    for (uint32_t m = threadIdx.x; m < P + 3; m += kEwThreads) {
+        uint32_t rem = m >= P ? m - P : m;
+        uint32_t off[NIN];
+#pragma unroll
+        for (int i = 0; i < NIN; i++) off[i] = 0;
+        for (int d = 0; d < a.n_inner; d++) {
+            uint32_t idx;
+            if (d == a.n_inner - 1) {
+                idx = rem;
+            } else {
+                const uint32_t qq = fdiv(rem, a.in_div[d]);
+                idx = rem - qq * a.in_ext[d];
+                rem = qq;
+            }
+#pragma unroll
+            for (int i = 0; i < NIN; i++) off[i] += idx * a.in_stride[i][d];
+        }
+#pragma unroll
+        for (int i = 0; i < NIN; i++) {
+            const int kind = KS[i] == 3 ? (int)a.kind[i] : KS[i];
+            if (kind != 0) {
+                const uint32_t val = kind == 1 ? __float_as_uint(__ldg(a.in[i] + off[i])) : off[i];
+#pragma unroll
+                for (uint32_t s = 0; s < 4; s++)
+                    if (m >= s) tbl[i][s][m - s] = val;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t n4 = a.n_items / 4;  // whole groups; the ragged one (if any) goes to one thread afterwards
+    for (uint32_t g = blockIdx.x * (uint32_t)kEwThreads + threadIdx.x; g < n4; g += gridDim.x * (uint32_t)kEwThreads)
+        per_group<F, K0, K1, K2, false>(a, f, tbl, 4 * g);
+    if ((a.n_items & 3u) && blockIdx.x == 0 && threadIdx.x == 0) per_group<F, K0, K1, K2, true>(a, f, tbl, 4 * n4);
 }
 
 // ---- tiled transpose kernel ----------------------------------------------------------------------
@@ -1003,6 +1261,73 @@ __global__ void __launch_bounds__(256) ew_outer_kernel(const OuterArgs a, const 
 }
 
 // ---- host-side launch plans ------------------------------------------------------------------------
+
+// Period plan (ew_period_kernel): 0 = not applicable, 1 = launched, -1 = error.
+template <typename F>
+static int try_launch_period(const F& f, const Folded& fo, const float* const* in, float* out, uint64_t n_items) {
+    constexpr int NIN = F::NIN;
+    uint64_t P = 1;
+    int g = 0;
+    while (g < fo.ndim && P * fo.extent[g] <= (uint64_t)kPerMax) P *= fo.extent[g++];
+    if (g == fo.ndim) return 0;
+    uint64_t split = 1;
+    for (uint64_t c = (uint64_t)kPerMax / P; c >= 2; c--)
+        if (fo.extent[g] % c == 0) {
+            split = c;
+            break;
+        }
+    P *= split;
+    if (P < 8) return 0;
+    PerArgs<NIN> a;
+    memset(&a, 0, sizeof a);
+    a.out = out;
+    a.n_items = (uint32_t)n_items;
+    a.period = (uint32_t)P;
+    a.period_div = make_fastdiv((uint32_t)P);
+    a.n_inner = g + (split > 1 ? 1 : 0);
+    a.n_outer = fo.ndim - g;
+    for (int d = 0; d < g; d++) a.in_ext[d] = (uint32_t)fo.extent[d];
+    if (split > 1) a.in_ext[g] = (uint32_t)split;
+    for (int d = 0; d < a.n_inner; d++) a.in_div[d] = make_fastdiv(a.in_ext[d]);
+    for (int d = g; d < fo.ndim; d++) {
+        a.out_ext[d - g] = (uint32_t)(d == g ? fo.extent[d] / split : fo.extent[d]);
+        a.out_div[d - g] = make_fastdiv(a.out_ext[d - g]);
+    }
+    for (int i = 0; i < NIN; i++) {
+        a.in[i] = in[i];
+        uint64_t span = 0;
+        bool congruent = (uintptr_t)in[i] % 16 == 0, periodic = true;
+        int64_t run = 1;
+        for (int d = 0; d < fo.ndim; d++) {
+            const int64_t st = fo.in_stride[i][d];
+            if (st < 0) return 0;
+            span += (fo.extent[d] - 1) * (uint64_t)st;
+            if (fo.extent[d] > 1 && st != run) congruent = false;
+            if (d >= g && st != 0) periodic = false;
+            run *= (int64_t)fo.extent[d];
+        }
+        if (span >= (1ull << 32)) return 0;
+        for (int d = 0; d < g; d++) a.in_stride[i][d] = (uint32_t)fo.in_stride[i][d];
+        if (split > 1) a.in_stride[i][g] = (uint32_t)fo.in_stride[i][g];
+        for (int d = g; d < fo.ndim; d++)
+            a.out_stride[i][d - g] = (uint32_t)(fo.in_stride[i][d] * (int64_t)(d == g ? split : 1));
+        a.kind[i] = congruent ? 0 : (periodic ? 1 : 2);
+    }
+    a.out_aligned = (uintptr_t)out % 16 == 0;
+    a.stream_store = n_items * sizeof(float) >= (uint64_t)rt().stream_store_min_bytes;
+    const uint64_t n4 = (n_items + 3) / 4;
+    uint64_t blocks = (n4 + kEwThreads - 1) / kEwThreads;
+    const uint64_t cap = (uint64_t)kNumSMs * 8;
+    if (blocks > cap) blocks = cap;
+    const int k0 = a.kind[0], k1 = NIN > 1 ? a.kind[1] : 3;
+    if (NIN == 1 && k0 == 2) ew_period_kernel<F, 2, 3, 3><<<(unsigned)blocks, kEwThreads, 0, rt().stream>>>(a, f);
+    else if (NIN == 2 && k0 == 2 && k1 == 1) ew_period_kernel<F, 2, 1, 3><<<(unsigned)blocks, kEwThreads, 0, rt().stream>>>(a, f);
+    else if (NIN == 2 && k0 == 1 && k1 == 2) ew_period_kernel<F, 1, 2, 3><<<(unsigned)blocks, kEwThreads, 0, rt().stream>>>(a, f);
+    else if (NIN == 2 && k0 == 2 && k1 == 2) ew_period_kernel<F, 2, 2, 3><<<(unsigned)blocks, kEwThreads, 0, rt().stream>>>(a, f);
+    else ew_period_kernel<F, 3, 3, 3><<<(unsigned)blocks, kEwThreads, 0, rt().stream>>>(a, f);
+    note_launch("ew_period");
+    return check_launch("ew_period") ? 1 : -1;
+}
 template <int VEC, typename F>
 static bool launch_nd_one(const F& f, const Folded& fo, const float* const* in, float* out, uint64_t n_items) {
     constexpr int NIN = F::NIN;
@@ -1085,6 +1410,12 @@ static bool launch_nd_one(const F& f, const Folded& fo, const float* const* in, 
             }
             a.blk_inner_div[i] = make_fastdiv(a.blk_inner[i]);
             a.blk_len_div[i] = make_fastdiv(a.blk_len[i]);
+        }
+        bool hard = false;  // some operand is outside ew_run's cheap addressing modes
+        for (int i = 0; i < NIN; i++) hard = hard || a.mode[i] == 2 || a.mode[i] == 3;
+        if (hard && rt().period_plan && !rt().force_general && fo.extent[0] <= 128) {
+            const int per = try_launch_period<F>(f, fo, in, out, n_items);
+            if (per != 0) return per > 0;
         }
         const uint64_t threads = (n_items + kRun - 1) / kRun;
         ew_run_kernel<F><<<(unsigned)((threads + kEwThreads - 1) / kEwThreads), kEwThreads, 0, s>>>(a, f);
@@ -1291,7 +1622,8 @@ static int try_launch_outer(const F& f, const Folded& fo, const float* const* in
     if constexpr (F::NIN != 2) {
         return 0;
     } else {
-        if (!rt().outer_tile || fo.ndim < 3) return 0;
+        // (a 4-element inner axis leaves one float4 per row: the tile's stores no longer coalesce and ew_nd is 20 % faster)
+        if (!rt().outer_tile || fo.ndim < 3 || fo.extent[0] < 8) return 0;
         int d1 = -1, d2 = -1;
         for (int d = 1; d < fo.ndim; d++) {
             if (fo.extent[d] < (uint64_t)kOT) continue;
@@ -1369,6 +1701,32 @@ static bool run_functor(const F& f, const EwCall& c, const Folded& fo) {
         if (s0 != 1 || (uintptr_t)in[i] % 16 != 0) vec_ok = false;
         for (int d = 1; d < fo.ndim && vec_ok; d++)
             if (fo.in_stride[i][d] % 4 != 0) vec_ok = false;
+    }
+    if constexpr (is_heavy<F>::value && NIN <= 2) {
+        bool flat = vec_ok && fo.ndim == 1 && fo.extent[0] >= 4 && fo.extent[0] / 4 < (1ull << 31) && rt().heavy_stream >= F::kHeavy;
+        for (int i = 0; i < NIN; i++) flat = flat && fo.in_stride[i][0] == 1;
+        if (flat) {
+            const uint64_t nb = fo.extent[0] & ~3ull, n4 = nb / 4;
+            uint64_t blocks = (n4 + (uint64_t)kEwThreads * kHeavyUnroll - 1) / ((uint64_t)kEwThreads * kHeavyUnroll);
+            static int resident = 0;  // CTAs of this instantiation that fit one SM (register-bound: 3..5)
+            if (resident == 0) {
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ew_heavy_stream_kernel<F>, kEwThreads, 0) != cudaSuccess || resident < 1)
+                    resident = 1;
+            }
+            const uint64_t cap = (uint64_t)kNumSMs * (uint64_t)(rt().heavy_ctas_per_sm > 0 ? rt().heavy_ctas_per_sm : resident);
+            if (blocks > cap) blocks = cap;
+            ew_heavy_stream_kernel<F><<<(unsigned)blocks, kEwThreads, 0, rt().stream>>>(
+                c.out, in[0], NIN == 2 ? in[NIN - 1] : nullptr, (uint32_t)n4, f,
+                nb * sizeof(float) >= (uint64_t)rt().stream_store_min_bytes);
+            note_launch("ew_heavy_stream");
+            if (!check_launch("ew_heavy_stream")) return false;
+            if (nb == fo.extent[0]) return true;
+            Folded tail = fo;
+            tail.extent[0] = fo.extent[0] - nb;
+            const float* in_tail[NIN];
+            for (int i = 0; i < NIN; i++) in_tail[i] = in[i] + nb;
+            return launch_nd<1, F>(f, tail, in_tail, c.out + nb);
+        }
     }
     if (vec_ok && fo.extent[0] % 4 == 0) {
         const int outer = try_launch_outer<F>(f, fo, in, c.out);

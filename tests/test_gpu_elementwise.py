@@ -412,3 +412,84 @@ def test_pow_and_log_fast_paths_match_glibc_bit_for_bit(al, orc, rng):
         for name, x in {"pos": rng.uniform(1e-30, 1e30, n).astype(np.float32), "near1": near_one(n), "normal": rng.standard_normal(n).astype(np.float32),
                         "bits": any_bits, "small": rng.uniform(0.0, 2.0, n).astype(np.float32)}.items():
             assert_bit_equal(al.to_numpy(al.log(al.from_numpy(x))), orc.unary("log", x), f"log {name}")
+
+
+@pytest.mark.parametrize("sa,sb", [((4001, 1, 7), (1, 9, 7)), ((301, 1, 3), (1, 257, 3)), ((33, 1, 5, 3), (1, 29, 1, 3)),
+                                   ((129, 1, 5, 3), (1, 64, 1, 3)), ((77, 1, 6), (1, 40, 6)), ((50, 5, 1, 3), (50, 1, 21, 3)),
+                                   ((9, 1, 2, 1, 3), (1, 11, 1, 13, 3)), ((1031, 1, 2), (1, 3, 2)), ((600, 1, 1), (1, 7, 5))])
+@pytest.mark.parametrize("op", ["sum", "div", "min", "ge"])
+def test_period_plan_is_used_and_exact(al, orc, rng, sa, sb, op):
+    """Short inner axes under operands outside ew_run's cheap addressing modes go through ew_period_kernel (values or
+    offsets of one period staged in shared memory, four shifted copies): bit-exact against the oracle and against
+    ew_run (period_plan=0), on aligned operands and on 4-byte shifted views with a ragged element count."""
+    from arraylib_b200._lib import lib
+    a, b = special_values(rng, sa), special_values(rng, sb)
+    A, B = al.from_numpy(a), al.from_numpy(b)
+    f = getattr(al, "add" if op == "sum" else op)
+    got = f(A, B)
+    used = lib.al_last_kernel().decode()
+    assert_bit_equal(al.to_numpy(got), orc.binary(op, a, b), f"{op} {sa} {sb}")
+    lib.al_set_tuning(b"period_plan", 0)
+    try:
+        slow = al.to_numpy(f(A, B))
+        assert lib.al_last_kernel().decode() != "ew_period"
+    finally:
+        lib.al_set_tuning(b"period_plan", 1)
+    assert_bit_equal(al.to_numpy(got), slow, "period plan vs ew_run")
+    if sa not in ((600, 1, 1), (301, 1, 3), (1031, 1, 2)):  # (a prime middle extent cannot be cut into periods: ew_run)
+        assert used == "ew_period", used
+    pa, pb = np.zeros(a.size + 1, np.float32), np.zeros(b.size + 1, np.float32)
+    pa[1:], pb[1:] = a.reshape(-1), b.reshape(-1)
+
+    def row_major(shape):
+        return tuple(int(np.prod(shape[i + 1:])) for i in range(len(shape)))
+
+    A2 = al.from_numpy(pa)[1:a.size + 1].as_strided(shape=sa, stride=row_major(sa))
+    B2 = al.from_numpy(pb)[1:b.size + 1].as_strided(shape=sb, stride=row_major(sb))
+    assert_bit_equal(al.to_numpy(f(A2, B2)), orc.binary(op, a, b), f"{op} {sa} {sb} shifted")
+
+
+def test_period_plan_permuted_views_and_unary(al, orc, rng):
+    """A permuted (non-contiguous) operand with a short axis, and a single hard operand under a unary / scalar op."""
+    x, y = rng.standard_normal((5, 300, 3)).astype(np.float32), rng.standard_normal((300, 1, 3)).astype(np.float32)
+    X = al.from_numpy(x).transpose((1, 0, 2))  # [300, 5, 3] with strides (3, 900, 1)
+    got = X + al.from_numpy(y)
+    assert_bit_equal(al.to_numpy(got), orc.binary("sum", np.ascontiguousarray(x.transpose(1, 0, 2)), y), "permuted operand")
+    xt = np.ascontiguousarray(x.transpose(1, 0, 2))
+    assert_bit_equal(al.to_numpy(X * 1.5), orc.binary("mul", xt, 1.5), "scalar op on a permuted view")
+    assert_bit_equal(al.to_numpy(al.copy(X, deep=True)), xt, "deep copy of a permuted view")
+    assert_bit_equal(al.to_numpy(al.sqrt(al.abs(X))), orc.unary("sqrt", orc.unary("abs", xt)), "unary on a permuted view")
+
+
+LIBM_DOMAINS = {
+    "exp": (-87.0, 87.0), "log": (1e-30, 1e30), "sin": (-200.0, 200.0), "cos": (-200.0, 200.0), "tan": (-200.0, 200.0),
+    "asin": (-1.0, 1.0), "acos": (-1.0, 1.0), "atan": (-50.0, 50.0), "sinh": (-20.0, 20.0), "cosh": (-20.0, 20.0),
+    "tanh": (-10.0, 10.0), "asinh": (-1e4, 1e4), "acosh": (1.0, 1e4), "atanh": (-1.0, 1.0),
+}
+
+
+@pytest.mark.parametrize("op", LIBM_UNARY)
+def test_libm_ufunc_fast_paths_match_glibc_bit_for_bit(al, orc, rng, op):
+    """csrc/fast_ufunc.h answers the elements whose float rounding is certain with a short FP64 kernel (validated on
+    the CPU against glibc over all 2^32 operands); the rest run CUDA's full double-precision routine. On the GPU, against
+    the oracle (glibc in double, rounded once: arraylib.c:31-49): 2^21 operands uniform over the function's domain, 2^21
+    normal operands, 2^21 operands next to 0 and 1 must be BIT-EXACT; over 2^21 random bit patterns (half of them outside
+    every fast path's range, i.e. CUDA's routine) at most 1 ulp on at most 1e-5 of the elements."""
+    n = 1 << 21
+    lo, hi = LIBM_DOMAINS[op]
+    near = np.concatenate([rng.standard_normal(n // 2).astype(np.float32) * np.float32(1e-3),
+                           (np.float32(1.0) + rng.integers(-4096, 4097, size=n // 2).astype(np.float32) * np.float32(2.0 ** -23)).astype(np.float32)])
+    mixes = {"uniform": rng.uniform(lo, hi, n).astype(np.float32), "normal": rng.standard_normal(n).astype(np.float32) * np.float32(2.0),
+             "near 0 and 1": near}
+    with np.errstate(all="ignore"):
+        for name, x in mixes.items():
+            got = al.to_numpy(getattr(al, op)(al.from_numpy(x)))
+            assert_bit_equal(got, orc.unary(op, x), f"{op} {name}")
+        x = rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32).view(np.float32)
+        got = al.to_numpy(getattr(al, op)(al.from_numpy(x)))
+        want = orc.unary(op, x)
+    nan = np.isnan(want)
+    assert np.array_equal(np.isnan(got), nan)
+    gi, wi = got[~nan].view(np.int32).astype(np.int64), want[~nan].view(np.int32).astype(np.int64)
+    ulp = np.abs(gi - wi)
+    assert ulp.max() <= 1 and (ulp != 0).mean() <= 1e-5, f"{op} any bits: max {ulp.max()} ulp, {(ulp != 0).sum()} differ"

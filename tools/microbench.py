@@ -332,9 +332,44 @@ def bench_ops():
     for name in ("add", "sub", "mul", "div", "mod", "pow", "max", "min", "eq", "ne", "gt", "ge", "lt", "le"):
         x = pos if name == "pow" else a
         timed(lambda: getattr(al, name)(x, b), 12 * n, f"binary {name} 2^28", reps=3, warm=1)
+    unit = al.sin(a)        # (-1, 1): the domain of asin / acos / atanh
+    above1 = pos + 0.5      # >= 1: acosh
     for name in ("neg", "abs", "sqrt", "exp", "log", "sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh",
                  "asinh", "acosh", "atanh", "ceil", "floor"):
-        timed(lambda: getattr(al, name)(pos), 8 * n, f"unary {name} 2^28", reps=3, warm=1)
+        x = unit if name in ("asin", "acos", "atanh") else above1 if name == "acosh" else pos if name in ("log", "sqrt") else a
+        timed(lambda: getattr(al, name)(x), 8 * n, f"unary {name} 2^28", reps=3, warm=1)
+
+
+def bench_heavy():
+    """FP64 ufuncs / pow on a contiguous stream: ew_nd (load, compute, store, exit) against the persistent kernel that
+    keeps the next batch's loads in flight while it computes."""
+    n = 1 << 28
+    a, b = rnd((n,), 1), rnd((n,), 2)
+    pos = al.abs(a) + 0.5
+    for name, x in (("exp", a), ("log", pos), ("sin", a), ("tanh", a), ("asinh", a), ("atan", a)):
+        for hs, ctas in ((0, 0), (2, 0), (2, 6)):
+            tune(heavy_stream=hs, heavy_ctas_per_sm=ctas)
+            timed(lambda: getattr(al, name)(x), 8 * n, f"unary {name} 2^28 heavy_stream={hs} ctas/SM={ctas or 'auto'}", reps=3, warm=1)
+    for hs, ctas in ((0, 0), (1, 0)):
+        tune(heavy_stream=hs, heavy_ctas_per_sm=ctas)
+        timed(lambda: al.pow(pos, b), 12 * n, f"binary pow 2^28 heavy_stream={hs} ctas/SM={ctas or 'auto'}", reps=3, warm=1)
+        timed(lambda: pos ** 1.5, 8 * n, f"scalar pow 2^28 heavy_stream={hs} ctas/SM={ctas or 'auto'}", reps=3, warm=1)
+    tune(heavy_stream=1, heavy_ctas_per_sm=0)
+
+
+def bench_period():
+    """Write-bound broadcasts with short inner axes: ew_run (period_plan=0) against the period-table kernel."""
+    cases = [((1 << 22, 1, 7), (1, 9, 7)), ((1 << 14, 1, 3), (1, 1 << 12, 3)), ((1 << 12, 1, 5, 3), (1, 1 << 11, 1, 3)),
+             ((1 << 20, 1, 6), (1, 40, 6)), ((1 << 16, 5, 1, 3), (1 << 16, 1, 100, 3)), ((4096, 1, 4096, 1), (1, 4, 1, 4))]
+    for sa, sb in cases:
+        A, B = rnd(sa, 1), rnd(sb, 2)
+        out_shape = np.broadcast_shapes(sa, sb)
+        nbytes = 4 * (int(np.prod(out_shape)) + int(np.prod(sa)) + int(np.prod(sb)))
+        for pp, ot in ((0, 1), (1, 1), (1, 0)):
+            tune(period_plan=pp, outer_tile=ot)
+            timed(lambda: A + B, nbytes, f"{sa} + {sb} period_plan={pp} outer_tile={ot}", reps=3, warm=1)
+        tune(period_plan=1, outer_tile=1)
+        del A, B
 
 
 if __name__ == "__main__":
