@@ -54,6 +54,7 @@ struct Runtime {
     long heavy_stream = 1;     // persistent prefetching kernel for contiguous streams: 0 never, 1 pow, 2 pow and the FP64 ufuncs
     long heavy_ctas_per_sm = 0;  // persistent CTAs per SM of ew_heavy_stream_kernel (0 = as many as are resident)
     long host_staging = 1;     // 0: pageable from_numpy / to_numpy use plain cudaMemcpy instead of the library's pinned ring + copy threads
+    long host_copy_nt = 1;     // 1: the staging ring's host copies use streaming stores (hostcopy.cpp), 0: memcpy
     long peer_collective = 1;  // 0: cross-GPU reductions go through ncclAllReduce instead of the peer-memory windows
 };
 Runtime& rt();

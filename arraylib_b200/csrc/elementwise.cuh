@@ -611,7 +611,10 @@ struct PerArgs {
     uint32_t in_ext[kMaxDims], out_ext[kMaxDims];
     FastDiv in_div[kMaxDims], out_div[kMaxDims];
     uint32_t in_stride[NIN][kMaxDims], out_stride[NIN][kMaxDims];  // element strides; every operand spans < 2^32 elements
-    unsigned char kind[NIN];  // 0: laid out like the output (128-bit loads), 1: values staged, 2: offsets staged
+    unsigned char kind[NIN];  // 0: laid out like the output (128-bit loads), 1: values staged, 2: offsets staged,
+                              // 4: contiguous with period blk_len (a multiple of 4, aligned base): offset = e mod blk_len, one 128-bit load
+    uint32_t blk_len[NIN];
+    FastDiv blk_len_div[NIN];
     unsigned char stream_store, out_aligned;
 };
 
@@ -636,30 +639,39 @@ __device__ __forceinline__ void per_outer_offsets(const PerArgs<NIN>& a, uint32_
     }
 }
 
-// One group of 4 consecutive outputs starting at e0. GUARD: the ragged last group (per-element bounds checks);
-// K0..K2: operand kinds known at compile time (3 = read a.kind[i]), which removes every per-operand branch from the loop.
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 t;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "r"(addr));
+    return t;
+}
+
+// Operand values of one group of 4 consecutive outputs starting at e0. GUARD: the ragged last group (per-element bounds
+// checks); K0..K2: operand kinds known at compile time (3 = read a.kind[i]), which removes every per-operand branch.
+// The table entries past the wrap (m >= P) of an offset table already contain the step of the first outer axis, so the
+// offset of an element is table + outer(q) unless the group wraps exactly where that outer axis carries (rare: fixed up).
 template <typename F, int K0, int K1, int K2, bool GUARD>
-__device__ __forceinline__ void per_group(const PerArgs<F::NIN>& a, const F& f, const uint32_t (*tbl)[4][kPerMax + 4], uint32_t e0) {
+__device__ __forceinline__ void per_load(const PerArgs<F::NIN>& a, uint32_t tbl_base, uint32_t e0, float (*v)[F::NIN]) {
     constexpr int NIN = F::NIN;
     constexpr int KS[3] = {K0, K1, K2};
     const uint32_t P = a.period;
     const uint32_t q = fdiv(e0, a.period_div), r = e0 - q * P;
     const uint32_t s = r & 3u, j = r - s;
-    uint32_t o0[NIN], o1[NIN];
-    if (a.n_outer == 1) {  // the usual case: one axis above the period
+    uint32_t o0[NIN];
+    bool fix = false;
+    if (a.n_outer == 1) {  // the usual case: one axis above the period, no carries
 #pragma unroll
-        for (int i = 0; i < NIN; i++) o0[i] = q * a.out_stride[i][0], o1[i] = o0[i] + a.out_stride[i][0];
+        for (int i = 0; i < NIN; i++) o0[i] = q * a.out_stride[i][0];
+    } else if (a.n_outer == 2) {  // two axes above the period (one of them usually the remainder of a split axis)
+        const uint32_t q1 = fdiv(q, a.out_div[0]), i0 = q - q1 * a.out_ext[0];
+#pragma unroll
+        for (int i = 0; i < NIN; i++) o0[i] = i0 * a.out_stride[i][0] + q1 * a.out_stride[i][1];
+        fix = r + 3 >= P && i0 == a.out_ext[0] - 1;
     } else {
         per_outer_offsets<NIN>(a, q, o0);
-        if (r + 3 >= P) {
-            per_outer_offsets<NIN>(a, q + 1, o1);
-        } else {
-#pragma unroll
-            for (int i = 0; i < NIN; i++) o1[i] = o0[i];
-        }
+        const uint32_t q1 = fdiv(q, a.out_div[0]);
+        fix = r + 3 >= P && q - q1 * a.out_ext[0] == a.out_ext[0] - 1;
     }
-    const uint32_t wrap = P - r;  // elements c >= wrap belong to the next period
-    float v[4][NIN];
+    const uint32_t row = tbl_base + s * (uint32_t)((kPerMax + 4) * 4) + j * 4u;
 #pragma unroll
     for (int i = 0; i < NIN; i++) {
         const int kind = KS[i] == 3 ? (int)a.kind[i] : KS[i];
@@ -672,19 +684,40 @@ __device__ __forceinline__ void per_group(const PerArgs<F::NIN>& a, const F& f, 
                 for (int c = 0; c < 4; c++)
                     if (e0 + c < a.n_items) v[c][i] = __ldg(a.in[i] + e0 + c);
             }
+        } else if (kind == 4) {
+            const uint32_t o = e0 - fdiv(e0, a.blk_len_div[i]) * a.blk_len[i];  // a multiple of 4; the group never wraps
+            if (!GUARD) {
+                const float4 d = __ldg(reinterpret_cast<const float4*>(a.in[i] + o));
+                v[0][i] = d.x, v[1][i] = d.y, v[2][i] = d.z, v[3][i] = d.w;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    if (e0 + c < a.n_items) v[c][i] = __ldg(a.in[i] + o + c);
+            }
         } else {
-            const uint4 t = *reinterpret_cast<const uint4*>(&tbl[i][s][j]);
-            const uint32_t tv[4] = {t.x, t.y, t.z, t.w};
+            const uint4 t = lds128(row + (uint32_t)(i * 4 * (kPerMax + 4) * 4));
+            uint32_t tv[4] = {t.x, t.y, t.z, t.w};
             if (kind == 1) {
 #pragma unroll
                 for (int c = 0; c < 4; c++) v[c][i] = __uint_as_float(tv[c]);
             } else {
+                if (fix) {  // elements past the wrap: drop the baked-in step, use the offsets of the next outer index
+                    uint32_t o1[NIN];
+                    per_outer_offsets<NIN>(a, q + 1, o1);
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+                        if (r + c >= P) tv[c] += o1[i] - o0[i] - a.out_stride[i][0];
+                }
 #pragma unroll
                 for (int c = 0; c < 4; c++)
-                    if (!GUARD || e0 + c < a.n_items) v[c][i] = __ldg(a.in[i] + (tv[c] + ((uint32_t)c >= wrap ? o1[i] : o0[i])));
+                    if (!GUARD || e0 + c < a.n_items) v[c][i] = __ldg(a.in[i] + (tv[c] + o0[i]));
             }
         }
     }
+}
+
+template <typename F, bool GUARD>
+__device__ __forceinline__ void per_store(const PerArgs<F::NIN>& a, const F& f, uint32_t e0, float (*v)[F::NIN]) {
     float* dst = a.out + e0;
     if (!GUARD) {
         // the bare arithmetic first; one NaN test for the four results (a NaN survives the sum; inf - inf only costs a
@@ -738,8 +771,8 @@ __global__ void __launch_bounds__(kEwThreads) ew_period_kernel(const PerArgs<F::
 #pragma unroll
         for (int i = 0; i < NIN; i++) {
             const int kind = KS[i] == 3 ? (int)a.kind[i] : KS[i];
-            if (kind != 0) {
-                const uint32_t val = kind == 1 ? __float_as_uint(__ldg(a.in[i] + off[i])) : off[i];
+            if (kind == 1 || kind == 2) {
+                const uint32_t val = kind == 1 ? __float_as_uint(__ldg(a.in[i] + off[i])) : off[i] + (m >= P ? a.out_stride[i][0] : 0u);
 #pragma unroll
                 for (uint32_t s = 0; s < 4; s++)
                     if (m >= s) tbl[i][s][m - s] = val;
@@ -747,10 +780,23 @@ __global__ void __launch_bounds__(kEwThreads) ew_period_kernel(const PerArgs<F::
         }
     }
     __syncthreads();
+    const uint32_t tbl_base = (uint32_t)__cvta_generic_to_shared(&tbl[0][0][0]);
     const uint32_t n4 = a.n_items / 4;  // whole groups; the ragged one (if any) goes to one thread afterwards
-    for (uint32_t g = blockIdx.x * (uint32_t)kEwThreads + threadIdx.x; g < n4; g += gridDim.x * (uint32_t)kEwThreads)
-        per_group<F, K0, K1, K2, false>(a, f, tbl, 4 * g);
-    if ((a.n_items & 3u) && blockIdx.x == 0 && threadIdx.x == 0) per_group<F, K0, K1, K2, true>(a, f, tbl, 4 * n4);
+    const uint32_t step = gridDim.x * (uint32_t)kEwThreads;
+    // two groups per trip, all gathers of both issued before the first use
+    for (uint32_t g = blockIdx.x * (uint32_t)kEwThreads + threadIdx.x; g < n4; g += 2 * step) {
+        float v0[4][NIN], v1[4][NIN];
+        const bool second = g + step < n4;
+        per_load<F, K0, K1, K2, false>(a, tbl_base, 4 * g, v0);
+        if (second) per_load<F, K0, K1, K2, false>(a, tbl_base, 4 * (g + step), v1);
+        per_store<F, false>(a, f, 4 * g, v0);
+        if (second) per_store<F, false>(a, f, 4 * (g + step), v1);
+    }
+    if ((a.n_items & 3u) && blockIdx.x == 0 && threadIdx.x == 0) {
+        float v[4][NIN];
+        per_load<F, K0, K1, K2, true>(a, tbl_base, 4 * n4, v);
+        per_store<F, true>(a, f, 4 * n4, v);
+    }
 }
 
 // ---- tiled transpose kernel ----------------------------------------------------------------------
@@ -1312,19 +1358,40 @@ static int try_launch_period(const F& f, const Folded& fo, const float* const* i
         for (int d = g; d < fo.ndim; d++)
             a.out_stride[i][d - g] = (uint32_t)(fo.in_stride[i][d] * (int64_t)(d == g ? split : 1));
         a.kind[i] = congruent ? 0 : (periodic ? 1 : 2);
+        if (a.kind[i] == 2 && (uintptr_t)in[i] % 16 == 0) {  // (a period that fits the table is cheaper from shared memory: kind 1)
+            // unit-stride over a leading run of axes and stride 0 above it (what broadcasting a contiguous array gives)
+            uint64_t len = 1;
+            int d2 = 0;
+            while (d2 < fo.ndim && (fo.in_stride[i][d2] == (int64_t)len || fo.extent[d2] == 1)) len *= fo.extent[d2++];
+            bool rest_zero = d2 > 0;
+            for (int d = d2; d < fo.ndim; d++) rest_zero = rest_zero && fo.in_stride[i][d] == 0;
+            if (rest_zero && len % 4 == 0 && len < (1ull << 31)) {
+                a.kind[i] = 4;
+                a.blk_len[i] = (uint32_t)len;
+                a.blk_len_div[i] = make_fastdiv((uint32_t)len);
+            }
+        }
     }
     a.out_aligned = (uintptr_t)out % 16 == 0;
     a.stream_store = n_items * sizeof(float) >= (uint64_t)rt().stream_store_min_bytes;
     const uint64_t n4 = (n_items + 3) / 4;
-    uint64_t blocks = (n4 + kEwThreads - 1) / kEwThreads;
-    const uint64_t cap = (uint64_t)kNumSMs * 8;
-    if (blocks > cap) blocks = cap;
+    const uint64_t want = (n4 + 2 * kEwThreads - 1) / (2 * kEwThreads);  // two groups per thread and trip
+    auto launch = [&](auto kernel) {
+        static int resident = 0;  // persistent CTAs: as many as fit one SM (register-bound, 6)
+        if (resident == 0) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, kEwThreads, 0) != cudaSuccess || resident < 1) resident = 1;
+        }
+        const uint64_t cap = (uint64_t)kNumSMs * (uint64_t)resident;
+        kernel<<<(unsigned)(want < cap ? want : cap), kEwThreads, 0, rt().stream>>>(a, f);
+    };
     const int k0 = a.kind[0], k1 = NIN > 1 ? a.kind[1] : 3;
-    if (NIN == 1 && k0 == 2) ew_period_kernel<F, 2, 3, 3><<<(unsigned)blocks, kEwThreads, 0, rt().stream>>>(a, f);
-    else if (NIN == 2 && k0 == 2 && k1 == 1) ew_period_kernel<F, 2, 1, 3><<<(unsigned)blocks, kEwThreads, 0, rt().stream>>>(a, f);
-    else if (NIN == 2 && k0 == 1 && k1 == 2) ew_period_kernel<F, 1, 2, 3><<<(unsigned)blocks, kEwThreads, 0, rt().stream>>>(a, f);
-    else if (NIN == 2 && k0 == 2 && k1 == 2) ew_period_kernel<F, 2, 2, 3><<<(unsigned)blocks, kEwThreads, 0, rt().stream>>>(a, f);
-    else ew_period_kernel<F, 3, 3, 3><<<(unsigned)blocks, kEwThreads, 0, rt().stream>>>(a, f);
+    if (NIN == 1 && k0 == 2) launch(ew_period_kernel<F, 2, 3, 3>);
+    else if (NIN == 2 && k0 == 2 && k1 == 1) launch(ew_period_kernel<F, 2, 1, 3>);
+    else if (NIN == 2 && k0 == 1 && k1 == 2) launch(ew_period_kernel<F, 1, 2, 3>);
+    else if (NIN == 2 && k0 == 2 && k1 == 2) launch(ew_period_kernel<F, 2, 2, 3>);
+    else if (NIN == 2 && k0 == 2 && k1 == 4) launch(ew_period_kernel<F, 2, 4, 3>);
+    else if (NIN == 2 && k0 == 4 && k1 == 2) launch(ew_period_kernel<F, 4, 2, 3>);
+    else launch(ew_period_kernel<F, 3, 3, 3>);
     note_launch("ew_period");
     return check_launch("ew_period") ? 1 : -1;
 }

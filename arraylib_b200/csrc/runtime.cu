@@ -380,6 +380,12 @@ bool fill_const(float* p, size_t n, float v) {
 // pinned slots: helper threads copy between the caller's buffer and a slot while the DMA engine moves the
 // previous slot, uploads and downloads use separate rings and streams (PCIe is full duplex), and the API lock is
 // NOT held while bytes move, so one host thread can upload while another downloads.
+extern "C" void al_host_copy_stream(char* dst, const char* src, size_t n);  // hostcopy.cpp: streaming (non-temporal) stores
+static inline void host_copy(char* dst, const char* src, size_t n) {
+    if (g_rt.host_copy_nt) al_host_copy_stream(dst, src, n);
+    else memcpy(dst, src, n);
+}
+
 struct CopyPool {
     struct Job {
         char* dst;
@@ -401,7 +407,7 @@ struct CopyPool {
                 j = q.front();
                 q.pop_front();
             }
-            memcpy(j.dst, j.src, j.n);
+            host_copy(j.dst, j.src, j.n);
             j.pending->fetch_sub(1, std::memory_order_release);
         }
     }
@@ -441,7 +447,7 @@ struct CopyPool {
             }
         }
         cv.notify_all();
-        memcpy(dst, src, std::min(each, n));
+        host_copy(dst, src, std::min(each, n));
         while (pending.load(std::memory_order_acquire) > 0) std::this_thread::yield();
     }
 };
@@ -694,6 +700,7 @@ int al_set_tuning(const char* key, long value) {
     else if (k == "reduce_sequential") g_rt.reduce_sequential = value;
     else if (k == "skip_zero_sign_fix") g_rt.skip_zero_sign_fix = value;
     else if (k == "host_staging") g_rt.host_staging = value;
+    else if (k == "host_copy_nt") g_rt.host_copy_nt = value;
     else if (k == "reduce_loads_per_lane") g_rt.reduce_loads_per_lane = value;
     else if (k == "disable_window") g_rt.disable_window = value;
     else if (k == "window_shfl") g_rt.window_shfl = value;
