@@ -454,7 +454,19 @@ struct CopyPool {
 static CopyPool* g_copy_pool = nullptr;  // leaked on purpose: detached helpers may outlive static destruction
 
 constexpr int kRingSlots = 3;
-constexpr size_t kRingSlotBytes = (size_t)32 << 20;
+// slot size of the staging rings: ARRAYLIB_RING_SLOT_MB (1..256), default 32 MiB
+static size_t ring_slot_bytes() {
+    static size_t bytes = 0;
+    if (bytes == 0) {
+        const char* env = getenv("ARRAYLIB_RING_SLOT_MB");
+        long mb = env ? atol(env) : 32;
+        if (mb < 1) mb = 1;
+        if (mb > 256) mb = 256;
+        bytes = (size_t)mb << 20;
+    }
+    return bytes;
+}
+#define kRingSlotBytes (ring_slot_bytes())
 constexpr size_t kStagedMinBytes = (size_t)4 << 20;  // smaller transfers: the driver's own staging is as good
 struct PinnedRing {
     std::mutex busy;  // one transfer per direction at a time

@@ -250,6 +250,29 @@ def bench_pcie():
     print(f"{'D2H 4 GiB pageable (fresh np.empty)':40s} {dt*1e3:8.1f} ms  {4*n/dt/1e9:6.1f} GB/s", flush=True)
 
 
+def bench_stock():
+    """The stock signatures on pageable numpy arrays: upload alone, download alone, both at once (second host thread)."""
+    import threading
+    import time
+    n = 1 << 28
+    src = np.ones(n, np.float32)
+    dst = np.empty(n, np.float32)
+    X = al.from_numpy(src)
+    al.synchronize()
+    best = {"up": 0.0, "down": 0.0, "both": 0.0}
+    for _ in range(3):
+        t0 = time.perf_counter(); Y = al.from_numpy(src); al.synchronize(); dt = time.perf_counter() - t0
+        best["up"] = max(best["up"], 4 * n / dt / 1e9)
+        t0 = time.perf_counter(); al.to_numpy(X, out=dst); dt = time.perf_counter() - t0
+        best["down"] = max(best["down"], 4 * n / dt / 1e9)
+        th = threading.Thread(target=lambda: al.to_numpy(X, out=dst))
+        t0 = time.perf_counter(); th.start(); Z = al.from_numpy(src); th.join(); al.synchronize(); dt = time.perf_counter() - t0
+        best["both"] = max(best["both"], 8 * n / dt / 1e9)
+        del Y, Z
+    print(f"stock API 1 GiB pageable: slot {os.environ.get('ARRAYLIB_RING_SLOT_MB', '32')} MiB, tuning {os.environ.get('ARRAYLIB_TUNING', '-')}, "
+          f"copy threads {os.environ.get('ARRAYLIB_COPY_THREADS', 'auto')}: upload {best['up']:.1f} GB/s, download {best['down']:.1f} GB/s, both {best['both']:.1f} GB/s total", flush=True)
+
+
 def bench_latency():
     """Host-side cost per op on tiny arrays (the C1 / README regime)."""
     import time

@@ -19,6 +19,12 @@ X5, Y5 = rnd((m, m), 5), rnd((m, m), 6)
 # shapes off the BASELINE configs that exercise the fallback kernels (ew_run modes, reduce_inner_peel, reduce_window_any)
 P3, p3 = rnd(((1 << 26) // scale, 3), 7), rnd((3,), 8)
 R255 = rnd(((1 << 20) // scale, 255), 9)
+# round 3: period-table kernel (short inner axes), odd-extent transpose (4-byte tile), FP64 ufuncs and pow
+PA, PB = rnd(((1 << 22) // scale, 1, 7), 10), rnd((1, 9, 7), 11)
+QA, QB = rnd((4096 // scale, 1, 5, 3), 12), rnd((1, 2048, 1, 3), 13)
+mo = m - 1
+XO = rnd((mo, mo), 14)
+pos = al.abs(a) + 0.5
 for rep in range(2):
     r = a + b; del r
     r = a * b; del r
@@ -35,5 +41,12 @@ for rep in range(2):
     r = P3 + p3; del r
     r = R255.reduce_sum(dims=(1,)); del r
     r = a.as_strided(shape=(n - 99, 100), stride=(1, 1)).reduce_sum(dims=[1]); del r
+    r = PA + PB; del r
+    r = QA + QB; del r
+    r = XO.transpose((1, 0)).reshape((mo * mo,)); del r
+    r = al.exp(a); del r
+    r = al.log(pos); del r
+    r = al.sin(a); del r
+    r = al.pow(pos, b); del r
 al.synchronize()
 print("profile_ops done")
