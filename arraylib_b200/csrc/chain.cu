@@ -53,7 +53,7 @@ __device__ __forceinline__ void lanes_bin(float* acc, const float* other, bool r
 template <int OP, int N>
 __device__ __forceinline__ void lanes_un(float* acc) {
 #pragma unroll
-    for (int c = 0; c < N; c++) acc[c] = ufunc_raw<OP>(acc[c]);
+    for (int c = 0; c < N; c++) acc[c] = ufunc_value<OP>(acc[c]);
 }
 
 template <bool FULL, int N>

@@ -124,6 +124,28 @@ __device__ __forceinline__ float binop_apply(float l, float r) {
 // The reference promotes to double, calls libm and rounds back (arraylib.c:31-49). sqrt/ceil/
 // floor/abs/neg are exact under that double rounding, so they stay in f32; the transcendentals
 // run in FP64 on the device and round once.
+// The certified fast path of a libm ufunc (fast_ufunc.h): true and *out when the float rounding of the result is certain
+// (bit-identical to the reference's glibc result, validated over all 2^32 operands on the CPU). Accepted results are
+// finite, so the NaN rules below never apply to them.
+template <int OP>
+__device__ __forceinline__ bool ufunc_fast(float v, float* out) {
+    if constexpr (OP == AL_EXP) return fu_fast_exp(v, out);
+    else if constexpr (OP == AL_LOG) return fu_fast_log(v, out);
+    else if constexpr (OP == AL_SIN) return fu_fast_sin(v, out);
+    else if constexpr (OP == AL_COS) return fu_fast_cos(v, out);
+    else if constexpr (OP == AL_TAN) return fu_fast_tan(v, out);
+    else if constexpr (OP == AL_ASIN) return fu_fast_asin(v, out);
+    else if constexpr (OP == AL_ACOS) return fu_fast_acos(v, out);
+    else if constexpr (OP == AL_ATAN) return fu_fast_atan(v, out);
+    else if constexpr (OP == AL_SINH) return fu_fast_sinh(v, out);
+    else if constexpr (OP == AL_COSH) return fu_fast_cosh(v, out);
+    else if constexpr (OP == AL_TANH) return fu_fast_tanh(v, out);
+    else if constexpr (OP == AL_ASINH) return fu_fast_asinh(v, out);
+    else if constexpr (OP == AL_ACOSH) return fu_fast_acosh(v, out);
+    else if constexpr (OP == AL_ATANH) return fu_fast_atanh(v, out);
+    else return false;
+}
+
 template <int OP>
 __device__ __forceinline__ float ufunc_raw(float v) {
     if constexpr (OP == AL_NEG) return flip_sign_bit(v);  // bitwise in the reference too (a NaN keeps its payload, unquieted)
@@ -132,26 +154,7 @@ __device__ __forceinline__ float ufunc_raw(float v) {
     else if constexpr (OP == AL_CEIL) return ceilf(v);
     else if constexpr (OP == AL_FLOOR) return floorf(v);
     else {
-        // fast_ufunc.h: short double-precision kernels, accepted when the float rounding of the result is certain
-        // (bit-identical to the reference's glibc result, validated over all 2^32 operands on the CPU); the other
-        // ~0.012 % of the elements and out-of-range operands run CUDA's full double-precision routine below
-        float fast = 0.0f;
-        bool have = false;
-        if constexpr (OP == AL_EXP) have = fu_fast_exp(v, &fast);
-        else if constexpr (OP == AL_LOG) have = fu_fast_log(v, &fast);
-        else if constexpr (OP == AL_SIN) have = fu_fast_sin(v, &fast);
-        else if constexpr (OP == AL_COS) have = fu_fast_cos(v, &fast);
-        else if constexpr (OP == AL_TAN) have = fu_fast_tan(v, &fast);
-        else if constexpr (OP == AL_ASIN) have = fu_fast_asin(v, &fast);
-        else if constexpr (OP == AL_ACOS) have = fu_fast_acos(v, &fast);
-        else if constexpr (OP == AL_ATAN) have = fu_fast_atan(v, &fast);
-        else if constexpr (OP == AL_SINH) have = fu_fast_sinh(v, &fast);
-        else if constexpr (OP == AL_COSH) have = fu_fast_cosh(v, &fast);
-        else if constexpr (OP == AL_TANH) have = fu_fast_tanh(v, &fast);
-        else if constexpr (OP == AL_ASINH) have = fu_fast_asinh(v, &fast);
-        else if constexpr (OP == AL_ACOSH) have = fu_fast_acosh(v, &fast);
-        else if constexpr (OP == AL_ATANH) have = fu_fast_atanh(v, &fast);
-        if (have) return fast;
+        // the ~0.012 % of the elements the fast path declines, and out-of-range operands: CUDA's full double routine
         double x = (double)v;
         if constexpr (OP == AL_EXP) x = exp(x);
         else if constexpr (OP == AL_LOG) x = log(x);
@@ -171,8 +174,22 @@ __device__ __forceinline__ float ufunc_raw(float v) {
     }
 }
 
+// the value as the fused chains compute it (fast path first, same as the eager kernels; a NaN is whatever the GPU makes of it)
+template <int OP>
+__device__ __forceinline__ float ufunc_value(float v) {
+    if constexpr (OP >= AL_EXP && OP <= AL_ATANH) {
+        float fast = 0.0f;
+        if (ufunc_fast<OP>(v, &fast)) return fast;
+    }
+    return ufunc_raw<OP>(v);
+}
+
 template <int OP>
 __device__ __forceinline__ float ufunc_apply(float v) {
+    if constexpr (OP >= AL_EXP && OP <= AL_ATANH) {
+        float fast = 0.0f;
+        if (ufunc_fast<OP>(v, &fast)) return fast;
+    }
     const float res = ufunc_raw<OP>(v);
     if constexpr (OP == AL_NEG) return res;
     if (res == res) return res;
@@ -311,8 +328,16 @@ __device__ __forceinline__ void store_vec(float* p, typename VecT<VEC>::type v, 
 
 constexpr int kEwThreads = 256;
 
+// Resident CTAs ptxas is asked to make room for: without a hint it chose 40 registers AND spills for the libm functors.
+// 5 CTAs (48 registers) fit every libm ufunc without a spill; pow needs 64.
+template <typename F>
+constexpr int ew_min_blocks() {
+    if constexpr (is_heavy<F>::value) return F::kHeavy == 2 ? 5 : 3;
+    else return 4;
+}
+
 template <int VEC, int UNROLL, typename F>
-__global__ void __launch_bounds__(kEwThreads) ew_nd_kernel(const NdArgs<F::NIN> a, const F f) {
+__global__ void __launch_bounds__(kEwThreads, ew_min_blocks<F>()) ew_nd_kernel(const NdArgs<F::NIN> a, const F f) {
     constexpr int NIN = F::NIN;
     using V = typename VecT<VEC>::type;
     const uint32_t base = blockIdx.x * (uint32_t)(kEwThreads * UNROLL) + threadIdx.x;

@@ -113,7 +113,7 @@ FP_HD void fu_cosh_sinh_small(double r, double* C, double* S) {
 
 // 2^(k/16 - 1) for -2000 <= k <= 2000
 FP_HD double fu_pow2_16th_half(int k) {
-    const double T = FU_POW2_16TH(k & 15);
+    const double T = FU_POW2_16TH((uint32_t)k & 15u);
     return FP_MAKE(FP_HI(T) + ((uint32_t)((k >> 4) - 1) << 20), FP_LO(T));
 }
 
@@ -154,9 +154,11 @@ FP_HD int fu_exponent_near_sqrt2(float y) {
     return (int)(b >> 23) - 127 + (int)((b & 0x007fffffu) > 0x003504f3u);
 }
 
-FP_HD int fu_finish(double r, float* out) {  // r a normal-float-range double: round, and say whether that rounding is certain
+// r a normal-float-range double: round, and say whether that rounding is certain, i.e. whether the 29 bits that the
+// conversion drops are at least 2^15 away from the tie 2^28 (three integer instructions)
+FP_HD int fu_finish(double r, float* out) {
     *out = (float)r;
-    return fp_boundary_distance(r) >= FU_ACCEPT_DIST;
+    return ((FP_LO(r) - (0x10000000u - FU_ACCEPT_DIST + 1u)) & 0x1fffffffu) >= 2u * FU_ACCEPT_DIST - 1u;
 }
 
 FP_HD uint32_t fu_abs_bits(float x) { uint32_t b; memcpy(&b, &x, 4); return b & 0x7fffffffu; }
@@ -170,10 +172,10 @@ FP_HD int fu_fast_exp(float x, float* out) {
     q = fma(q, r, FU_K(FU_EX + 2));
     q = fma(q, r, FU_K(FU_EX + 3));
     q = fma(q, r, FU_K(FU_EX + 4));
-    const double T = FU_POW2_16TH(k & 15);
+    const double T = FU_POW2_16TH((uint32_t)k & 15u);
     const double v = fma(T, r * q, T);
     const double res = FP_MAKE(FP_HI(v) + ((uint32_t)(k >> 4) << 20), FP_LO(v));
-    return fu_finish(res, out) & (fu_abs_bits(x) <= 0x42ae0000u);  // |x| <= 87: the result is a normal float
+    return fu_finish(res, out) & (fabsf(x) <= 87.0f);  // |x| <= 87: the result is a normal float
 }
 
 // sinh = (P - Q) C + (P + Q) r S, cosh = (P + Q) C + (P - Q) r S with P = 2^(k/16 - 1), Q = 2^(-k/16 - 1); k == 0
@@ -184,9 +186,9 @@ FP_HD int fu_fast_sinh(float x, float* out) {
     fu_cosh_sinh_small(r, &C, &S);
     const double P = fu_pow2_16th_half(k), Q = fu_pow2_16th_half(-k);
     const double res = fma(P - Q, C, (P + Q) * (r * S));
-    const uint32_t ab = fu_abs_bits(x);
-    const int ok = fu_finish(res, out) & (ab <= 0x42ae0000u);
-    if (ab < 0x38800000u) { *out = x; return 1; }  // |x| < 2^-14: x (1 + x^2/6) rounds to x
+    const float ab = fabsf(x);
+    const int ok = fu_finish(res, out) & (ab <= 87.0f);
+    if (ab < 0x1p-14f) { *out = x; return 1; }  // |x| < 2^-14: x (1 + x^2/6) rounds to x
     return ok;
 }
 
@@ -196,7 +198,7 @@ FP_HD int fu_fast_cosh(float x, float* out) {
     fu_cosh_sinh_small(r, &C, &S);
     const double P = fu_pow2_16th_half(k), Q = fu_pow2_16th_half(-k);
     const double res = fma(P + Q, C, (P - Q) * (r * S));
-    return fu_finish(res, out) & (fu_abs_bits(x) <= 0x42ae0000u);
+    return fu_finish(res, out) & (fabsf(x) <= 87.0f);
 }
 
 FP_HD int fu_fast_tanh(float x, float* out) {
@@ -206,10 +208,10 @@ FP_HD int fu_fast_tanh(float x, float* out) {
     const double P = fu_pow2_16th_half(k), Q = fu_pow2_16th_half(-k);
     const double amb = P - Q, apb = P + Q, rS = r * S;
     const double res = fu_div(fma(amb, C, apb * rS), fma(apb, C, amb * rS));
-    const uint32_t ab = fu_abs_bits(x);
-    const int ok = fu_finish(res, out) & (ab < 0x41180000u);  // |x| < 9.5
-    if (ab < 0x38800000u) { *out = x; return 1; }            // x (1 - x^2/3) rounds to x
-    if (ab >= 0x41180000u && ab <= 0x7f800000u) {            // 1 - 2 exp(-2|x|) rounds to 1 from |x| = 9.02 on
+    const float ab = fabsf(x);
+    const int ok = fu_finish(res, out) & (ab < 9.5f);  // |x| < 9.5
+    if (ab < 0x1p-14f) { *out = x; return 1; }            // x (1 - x^2/3) rounds to x
+    if (ab >= 9.5f) {                                                    // 1 - 2 exp(-2|x|) rounds to 1 from |x| = 9.02 on
         *out = x < 0.0f ? -1.0f : 1.0f;
         return 1;
     }
@@ -229,26 +231,25 @@ FP_HD double fu_log_core(double v) {
 }
 
 FP_HD int fu_fast_log(float x, float* out) {
-    uint32_t xb; memcpy(&xb, &x, 4);
     const double r = fu_log_core((double)x);
-    return fu_finish(r, out) & (xb >= 0x00800000u) & (xb < 0x7f800000u);  // positive, normal, finite (log 1 = +0 passes)
+    return fu_finish(r, out) & (x >= 0x1p-126f) & (x <= 3.402823466e38f);  // positive, normal, finite (log 1 = +0 passes)
 }
 
 FP_HD int fu_fast_atanh(float x, float* out) {
-    const uint32_t ab = fu_abs_bits(x);
+    const float ab = fabsf(x);
     const double d = (double)x;
     const double N = 1.0 + d, D = 1.0 - d;                    // exact for 2^-14 <= |x| < 1
     const int j = fu_exponent_near_sqrt2((1.0f + x) * FU_RCP32(1.0f - x));
     const double Dj = FP_MAKE(FP_HI(D) + ((uint32_t)j << 20), FP_LO(D));
     const double s = fu_div(N - Dj, N + Dj);
     const double r = fma((double)j, FU_K(FU_LN2_HALF), fu_atanh_small(s));
-    const int ok = fu_finish(r, out) & (ab < 0x3f800000u);
-    if (ab < 0x38800000u) { *out = x; return 1; }             // x (1 + x^2/3) rounds to x
+    const int ok = fu_finish(r, out) & (ab < 1.0f);
+    if (ab < 0x1p-14f) { *out = x; return 1; }             // x (1 + x^2/3) rounds to x
     return ok;
 }
 
 FP_HD int fu_fast_asinh(float x, float* out) {
-    const uint32_t ab = fu_abs_bits(x);
+    const float ab = fabsf(x);
     const double a = fabs((double)x);
     const double u = fu_sqrt(fma(a, a, 1.0));
     const double N = a + u;
@@ -259,20 +260,19 @@ FP_HD int fu_fast_asinh(float x, float* out) {
     const double den = j == 0 ? fma(2.0, u, 2.0) : (a + P) + u;
     double r = fu_twice(fma((double)j, FU_K(FU_LN2_HALF), fu_atanh_small(fu_div(num, den))));
     r = FP_MAKE(FP_HI(r) | (x < 0.0f ? 0x80000000u : 0u), FP_LO(r));
-    const int ok = fu_finish(r, out) & (ab <= 0x5d800000u);   // |x| <= 2^60 (a^2 + 1 stays inside the float range)
-    if (ab < 0x38800000u) { *out = x; return 1; }             // x (1 - x^2/6) rounds to x
+    const int ok = fu_finish(r, out) & (ab <= 0x1p60f);   // |x| <= 2^60 (a^2 + 1 stays inside the float range)
+    if (ab < 0x1p-14f) { *out = x; return 1; }             // x (1 - x^2/6) rounds to x
     return ok;
 }
 
 FP_HD int fu_fast_acosh(float x, float* out) {
-    uint32_t xb; memcpy(&xb, &x, 4);
     const double d = (double)x;
     const double u = fu_sqrt(fma(d, d, -1.0));                // x^2 - 1 with one rounding
     const double N = d + u;
     const int j = fu_exponent_near_sqrt2((float)N);
     const double P = fu_pow2(j);
     const double r = fu_twice(fma((double)j, FU_K(FU_LN2_HALF), fu_atanh_small(fu_div((d - P) + u, (d + P) + u))));
-    return fu_finish(r, out) & (xb > 0x3f800000u) & (xb <= 0x5d800000u);  // 1 < x <= 2^60
+    return fu_finish(r, out) & (x > 1.0f) & (x <= 0x1p60f);  // 1 < x <= 2^60
 }
 
 // ---- sin, cos, tan ----------------------------------------------------------------------------------------------------
@@ -291,31 +291,31 @@ FP_HD double fu_sin_half_pi(double r) {
 
 // k = round(x / pi) in float arithmetic: for |x| <= 32768 the product is off by < 0.0013, i.e. |r| <= pi/2 + 0.004
 FP_HD int fu_fast_sin(float x, float* out) {
-    const uint32_t ab = fu_abs_bits(x);
+    const float ab = fabsf(x);
     const float t = fmaf(x, 0.31830987f, FU_MAGIC32);
     uint32_t k; memcpy(&k, &t, 4);
     const double kf = (double)(t - FU_MAGIC32);
     const double r = fma(-kf, FU_K(FU_PI_LO), fma(-kf, FU_K(FU_PI_HI), (double)x));
     const double v = fu_sin_half_pi(r);
     const double res = FP_MAKE(FP_HI(v) ^ (k << 31), FP_LO(v));
-    const int ok = fu_finish(res, out) & (ab <= 0x47000000u) & ((FP_HI(v) & 0x7ff00000u) > 0x39000000u);  // |x| <= 32768, |result| > 2^-110
-    if (ab < 0x38800000u) { *out = x; return 1; }  // x (1 - x^2/6) rounds to x
+    const int ok = fu_finish(res, out) & (ab <= 32768.0f) & ((FP_HI(v) & 0x7ff00000u) > 0x39000000u);  // |x| <= 32768, |result| > 2^-110
+    if (ab < 0x1p-14f) { *out = x; return 1; }  // x (1 - x^2/6) rounds to x
     return ok;
 }
 
 FP_HD int fu_fast_cos(float x, float* out) {
-    const uint32_t ab = fu_abs_bits(x);
+    const float ab = fabsf(x);
     const float t = fmaf(x, 0.31830987f, 0.5f) + FU_MAGIC32;  // k = round(x/pi + 1/2): cos x = (-1)^k sin(x - (k - 1/2) pi)
     uint32_t k; memcpy(&k, &t, 4);
     const double jf = (double)((t - FU_MAGIC32) - 0.5f);
     const double r = fma(-jf, FU_K(FU_PI_LO), fma(-jf, FU_K(FU_PI_HI), (double)x));
     const double v = fu_sin_half_pi(r);
     const double res = FP_MAKE(FP_HI(v) ^ (k << 31), FP_LO(v));
-    return fu_finish(res, out) & (ab <= 0x47000000u) & ((FP_HI(v) & 0x7ff00000u) > 0x39000000u);
+    return fu_finish(res, out) & (ab <= 32768.0f) & ((FP_HI(v) & 0x7ff00000u) > 0x39000000u);
 }
 
 FP_HD int fu_fast_tan(float x, float* out) {
-    const uint32_t ab = fu_abs_bits(x);
+    const float ab = fabsf(x);
     const float t = fmaf(x, 0.63661975f, FU_MAGIC32);
     uint32_t k; memcpy(&k, &t, 4);
     const double kf = (double)(t - FU_MAGIC32);
@@ -336,9 +336,9 @@ FP_HD int fu_fast_tan(float x, float* out) {
     const int odd = (int)(k & 1u);
     const double num = odd ? -cs : sn, den = odd ? sn : cs;   // tan(r + k pi/2) = -cot r for odd k
     const double res = fu_div(num, den);
-    const int ok = fu_finish(res, out) & (ab <= 0x47000000u) & ((FP_HI(res) & 0x7ff00000u) > 0x39000000u) &
+    const int ok = fu_finish(res, out) & (ab <= 32768.0f) & ((FP_HI(res) & 0x7ff00000u) > 0x39000000u) &
                    ((FP_HI(res) & 0x7ff00000u) < 0x47000000u);
-    if (ab < 0x38800000u) { *out = x; return 1; }  // x (1 + x^2/3) rounds to x
+    if (ab < 0x1p-14f) { *out = x; return 1; }  // x (1 + x^2/3) rounds to x
     return ok;
 }
 
@@ -361,40 +361,40 @@ FP_HD double fu_atan_ratio(double X, double Y, float Xf, float Yf) {
 }
 
 FP_HD int fu_fast_atan(float x, float* out) {
-    const uint32_t ab = fu_abs_bits(x);
+    const float ab = fabsf(x);
     const float af = fabsf(x);
     const double a = (double)af;
     const int inv = af > 1.0f;  // atan(a) = pi/2 - atan(1/a)
     const double h = fu_atan_ratio(inv ? 1.0 : a, inv ? a : 1.0, inv ? 1.0f : af, inv ? af : 1.0f);
     double r = inv ? FU_K(FU_PIO2_HI) - h : h;
     r = FP_MAKE(FP_HI(r) | (x < 0.0f ? 0x80000000u : 0u), FP_LO(r));
-    const int ok = fu_finish(r, out) & (ab < 0x7f800000u);
-    if (ab < 0x38800000u) { *out = x; return 1; }  // x (1 - x^2/3) rounds to x
+    const int ok = fu_finish(r, out) & (ab <= 3.402823466e38f);
+    if (ab < 0x1p-14f) { *out = x; return 1; }  // x (1 - x^2/3) rounds to x
     return ok;
 }
 
 // asin(x) = 2 atan(x / (1 + sqrt(1 - x^2))), acos(x) = 2 atan(sqrt(1 - x^2) / (1 + x)) for x >= 0, pi - acos(-x) below
 FP_HD int fu_fast_asin(float x, float* out) {
-    const uint32_t ab = fu_abs_bits(x);
+    const float ab = fabsf(x);
     const float af = fabsf(x);
     const double a = (double)af;
     const double u = fu_sqrt(fma(-a, a, 1.0));  // 1 - x^2 with one rounding
     const double w = 1.0 + u;
     double r = fu_twice(fu_atan_ratio(a, w, af, (float)w));
     r = FP_MAKE(FP_HI(r) | (x < 0.0f ? 0x80000000u : 0u), FP_LO(r));
-    const int ok = fu_finish(r, out) & (ab < 0x3f800000u);
-    if (ab < 0x38800000u) { *out = x; return 1; }  // x (1 + x^2/6) rounds to x
+    const int ok = fu_finish(r, out) & (ab < 1.0f);
+    if (ab < 0x1p-14f) { *out = x; return 1; }  // x (1 + x^2/6) rounds to x
     return ok;
 }
 
 FP_HD int fu_fast_acos(float x, float* out) {
-    const uint32_t ab = fu_abs_bits(x);
+    const float ab = fabsf(x);
     const float af = fabsf(x);
     const double a = (double)af;
     const double u = fu_sqrt(fma(-a, a, 1.0));
     const double w = 1.0 + a;
     const double h = fu_atan_ratio(u, w, (float)u, (float)w);
     const double r = x < 0.0f ? fma(-2.0, h, FU_K(FU_PI_HI)) : fu_twice(h);
-    return fu_finish(r, out) & (ab < 0x3f800000u);
+    return fu_finish(r, out) & (ab < 1.0f);
 }
 #endif
