@@ -61,10 +61,10 @@ static inline float fu_perturb_(float v, float x) {  // deterministic +-2^-21 re
       0.34657359027997264 /* ln(2) / 2 */,                                                                              \
       /* 44: (atan(t)/t - 1)/z on |t| <= 0.225, degree 5 */ 0.06759140727306162, -0.09039176935474555,                   \
       0.11109770226062675, -0.14285698480760142, 0.19999999931636747, -0.333333333332853,                               \
-      0.4124104415973873 /* atan(7/16) */, 0.7853981633974483 /* atan(1) */ }
+      0.4124104415973873 /* atan(7/16) */, 0.7853981633974483 /* atan(1) */, 23.083120654223414 /* 16 / ln 2 */ }
 enum { FU_EX = 0, FU_CH = 5, FU_SH = 8, FU_LG = 11, FU_SN = 16, FU_S4 = 23, FU_C4 = 28, FU_LN2_16 = 34, FU_LN2 = 35, FU_MAGIC = 36,
        FU_INVPI = 37, FU_PI_HI = 38, FU_PI_LO = 39, FU_2OPI = 40, FU_PIO2_HI = 41, FU_PIO2_LO = 42, FU_LN2_HALF = 43,
-       FU_AT = 44, FU_ATAN_C1 = 50, FU_ATAN_1 = 51, FU_NCONST = 52 };
+       FU_AT = 44, FU_ATAN_C1 = 50, FU_ATAN_1 = 51, FU_16_LN2 = 52, FU_NCONST = 53 };
 // 2^(j/16): read with per-lane indices, so it lives in global memory (one 128-byte line, L1-resident) instead of the
 // constant bank, where divergent indices would serialise
 #define FU_T16 { 1.0, 1.0442737824274138, 1.0905077326652577, 1.1387886347566916, 1.189207115002721, 1.241857812073484,  \
@@ -83,19 +83,17 @@ static const double fu_host_t16[16] = FU_T16;
 #define FU_K(i) fu_host_consts[i]
 #define FU_POW2_16TH(j) fu_host_t16[j]
 #endif
-#define FU_MAGIC32 12582912.0f  // 1.5 * 2^23: adding it rounds a float to an integer held in the low mantissa bits
 
 #define FU_ACCEPT_DIST (1u << 15)  // 2^15 units of the double's last place = 2^-37 relative
 
 
-// k = round(x * 16/ln 2) in float arithmetic (|x| <= 88: the product is off by < 2^-12, which only widens |r| by
-// 1e-5), r = x - k ln2/16 in double (|r| <= 0.02167): exp(x) = 2^(k >> 4) * 2^((k & 15)/16) * exp(r)
+// k = round(x * 16/ln 2) (magic-number rounding in double: DFMA + DADD, one issue slot fewer than the float variant with
+// its conversion), r = x - k ln2/16 (|r| <= 0.02167): exp(x) = 2^(k >> 4) * 2^((k & 15)/16) * exp(r)
 FP_HD int fu_exp_reduce(float x, double* R) {
-    const float t = fmaf(x, 23.083120654223414f, FU_MAGIC32);
-    uint32_t tb; memcpy(&tb, &t, 4);
-    const float kf = t - FU_MAGIC32;
-    *R = fma(-(double)kf, FU_K(FU_LN2_16), (double)x);
-    return (int)(tb - 0x4b400000u);
+    const double d = (double)x, magic = FU_K(FU_MAGIC);
+    const double kd = fma(d, FU_K(FU_16_LN2), magic);
+    *R = fma(-(kd - magic), FU_K(FU_LN2_16), d);
+    return (int)FP_LO(kd);
 }
 
 // cosh(r) and sinh(r)/r on the reduced range
@@ -289,37 +287,39 @@ FP_HD double fu_sin_half_pi(double r) {
     return fma(r * z, p, r);
 }
 
-// k = round(x / pi) in float arithmetic: for |x| <= 32768 the product is off by < 0.0013, i.e. |r| <= pi/2 + 0.004
+// k = round(x / pi) by magic-number rounding in double, two-constant Cody-Waite reduction, one polynomial on |r| <= pi/2.
+// Operands up to 32768; over that range |sin x|, |cos x| >= 4.1e-9 and |tan x| <= 2.4e8 for every float (exhaustive
+// scan), so the results are normal floats and need no range test of their own.
 FP_HD int fu_fast_sin(float x, float* out) {
     const float ab = fabsf(x);
-    const float t = fmaf(x, 0.31830987f, FU_MAGIC32);
-    uint32_t k; memcpy(&k, &t, 4);
-    const double kf = (double)(t - FU_MAGIC32);
-    const double r = fma(-kf, FU_K(FU_PI_LO), fma(-kf, FU_K(FU_PI_HI), (double)x));
+    const double d = (double)x, magic = FU_K(FU_MAGIC);
+    const double kd = fma(d, FU_K(FU_INVPI), magic);
+    const double kf = kd - magic;
+    const double r = fma(-kf, FU_K(FU_PI_LO), fma(-kf, FU_K(FU_PI_HI), d));
     const double v = fu_sin_half_pi(r);
-    const double res = FP_MAKE(FP_HI(v) ^ (k << 31), FP_LO(v));
-    const int ok = fu_finish(res, out) & (ab <= 32768.0f) & ((FP_HI(v) & 0x7ff00000u) > 0x39000000u);  // |x| <= 32768, |result| > 2^-110
+    const double res = FP_MAKE(FP_HI(v) ^ (FP_LO(kd) << 31), FP_LO(v));
+    const int ok = fu_finish(res, out) & (ab <= 32768.0f);
     if (ab < 0x1p-14f) { *out = x; return 1; }  // x (1 - x^2/6) rounds to x
     return ok;
 }
 
 FP_HD int fu_fast_cos(float x, float* out) {
-    const float ab = fabsf(x);
-    const float t = fmaf(x, 0.31830987f, 0.5f) + FU_MAGIC32;  // k = round(x/pi + 1/2): cos x = (-1)^k sin(x - (k - 1/2) pi)
-    uint32_t k; memcpy(&k, &t, 4);
-    const double jf = (double)((t - FU_MAGIC32) - 0.5f);
-    const double r = fma(-jf, FU_K(FU_PI_LO), fma(-jf, FU_K(FU_PI_HI), (double)x));
+    const double d = (double)x, magic = FU_K(FU_MAGIC);
+    const double kd = fma(d, FU_K(FU_INVPI), 0.5) + magic;   // k = round(x/pi + 1/2): cos x = (-1)^k sin(x - (k - 1/2) pi)
+    const double jf = (kd - magic) - 0.5;
+    const double r = fma(-jf, FU_K(FU_PI_LO), fma(-jf, FU_K(FU_PI_HI), d));
     const double v = fu_sin_half_pi(r);
-    const double res = FP_MAKE(FP_HI(v) ^ (k << 31), FP_LO(v));
-    return fu_finish(res, out) & (ab <= 32768.0f) & ((FP_HI(v) & 0x7ff00000u) > 0x39000000u);
+    const double res = FP_MAKE(FP_HI(v) ^ (FP_LO(kd) << 31), FP_LO(v));
+    return fu_finish(res, out) & (fabsf(x) <= 32768.0f);
 }
 
 FP_HD int fu_fast_tan(float x, float* out) {
     const float ab = fabsf(x);
-    const float t = fmaf(x, 0.63661975f, FU_MAGIC32);
-    uint32_t k; memcpy(&k, &t, 4);
-    const double kf = (double)(t - FU_MAGIC32);
-    const double r = fma(-kf, FU_K(FU_PIO2_LO), fma(-kf, FU_K(FU_PIO2_HI), (double)x));
+    const double d = (double)x, magic = FU_K(FU_MAGIC);
+    const double kd = fma(d, FU_K(FU_2OPI), magic);
+    const uint32_t k = FP_LO(kd);
+    const double kf = kd - magic;
+    const double r = fma(-kf, FU_K(FU_PIO2_LO), fma(-kf, FU_K(FU_PIO2_HI), d));
     const double z = r * r;
     double s = FU_K(FU_S4);
     s = fma(s, z, FU_K(FU_S4 + 1));
@@ -336,8 +336,7 @@ FP_HD int fu_fast_tan(float x, float* out) {
     const int odd = (int)(k & 1u);
     const double num = odd ? -cs : sn, den = odd ? sn : cs;   // tan(r + k pi/2) = -cot r for odd k
     const double res = fu_div(num, den);
-    const int ok = fu_finish(res, out) & (ab <= 32768.0f) & ((FP_HI(res) & 0x7ff00000u) > 0x39000000u) &
-                   ((FP_HI(res) & 0x7ff00000u) < 0x47000000u);
+    const int ok = fu_finish(res, out) & (ab <= 32768.0f);
     if (ab < 0x1p-14f) { *out = x; return 1; }  // x (1 + x^2/3) rounds to x
     return ok;
 }
