@@ -333,7 +333,7 @@ constexpr int kEwThreads = 256;
 template <typename F>
 constexpr int ew_min_blocks() {
     if constexpr (is_heavy<F>::value) return F::kHeavy == 2 ? 5 : 3;
-    else return 4;
+    else return 0;  // 0 = no hint: the streaming functors compile exactly as before
 }
 
 template <int VEC, int UNROLL, typename F>
