@@ -257,8 +257,12 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const float* __restrict_
 template <int OP>
 __device__ __forceinline__ float comb(float a, float b) {
     if constexpr (OP == AL_RSUM) return __fadd_rn(a, b);
-    else if constexpr (OP == AL_RMAX) return fmaxf(a, b);
-    else if constexpr (OP == AL_RMIN) return fminf(a, b);
+    // max / min like the reference's fold (gcc's inline fmax / fmin, arraylib.c:18-19): NaNs are ignored and a tie --
+    // +0 against -0 -- keeps the LEFT operand. Partials are combined in rank order = logical order of the leading axis,
+    // and every partial already carries the sign of ITS first zero (reduce_zero_sign_kernel), so the result has the sign
+    // of the first zero of the whole reduced set, exactly as on one GPU.
+    else if constexpr (OP == AL_RMAX) return (b != b) ? a : ((a != a) ? b : (a >= b ? a : b));
+    else if constexpr (OP == AL_RMIN) return (b != b) ? a : ((a != a) ? b : (a <= b ? a : b));
     else return __fmul_rn(a, b);
 }
 
@@ -540,8 +544,9 @@ static NDArray* comm_reduce(int redop, const NDArray* shard, const size_t* dims,
     if (peer_begin(nout, &map)) {
         // local kernel -> owners' slots over NVLink -> rank-ordered combine -> result on every rank (or, scatter: the
         // own segment only)
+        // (max / min go through the ordinary local reduce: its zero-sign repair pass must run before the partial leaves)
         bool fused = false;
-        if (!reduce_into_peers(redop, shard, dims, ndims, map, &fused)) return nullptr;
+        if (redop != AL_RMAX && redop != AL_RMIN && !reduce_into_peers(redop, shard, dims, ndims, map, &fused)) return nullptr;
         if (!fused) {
             NDArray* part = reduce_impl(redop, shard, dims, ndims, 0.0f, false);
             if (!part) return nullptr;

@@ -112,6 +112,17 @@ for shape, dims, op in [((L, 7, 13), (0,), "sum"), ((L, 7, 13), (0,), "max"), ((
         got = al.to_numpy(dist.reduce_sharded(Gs, op, dims))
         check(f"peer {op} {shape} {dims} #{rep}", got, orc.reduce(op, G, dims))
         same_on_all_ranks(f"peer {op} {shape} {dims}", got)
+# zero-sign rule across GPUs: the extreme value is a zero and the set holds +0 and -0 -> the FIRST zero in logical order
+# (fmax / fmin keep their left operand on a tie); columns differ in which rank holds the first zero and with which sign
+Z = np.where(rng.random((L, 3, 96)) < 0.5, np.float32(-0.0), np.float32(0.0)).astype(np.float32)
+Z[rng.random(Z.shape) < 0.3] = np.float32(-3.0)
+Z[:, :, :8] = np.float32(-3.0)       # columns whose maximum is not a zero at all
+for op, data in (("max", Z), ("min", -Z)):
+    Zs = dist.scatter_from_numpy(data)
+    for dims in ((0,), (0, 1)):
+        got = al.to_numpy(dist.reduce_sharded(Zs, op, dims))
+        check(f"peer {op} zero sign {dims}", got, orc.reduce(op, data, dims))
+        same_on_all_ranks(f"peer {op} zero sign {dims}", got)
 # in-place allreduce of an already materialised array (same windows: push, combine, collect)
 for n_el in (1, 5, 4096, 100003):
     parts = rng.integers(-8, 9, size=(world, n_el)).astype(np.float32)
