@@ -17,8 +17,14 @@
 //                    extents that are not multiples of 4.
 //   ew_interleave /  the same with a short, densely packed axis ([N,3] <-> [3,N]); ew_tile_rect for
 //   ew_deinterleave  short axes that are not packed.
-//   ew_run           anything else: 4 consecutive outputs per thread, linear index resolved once and
-//                    stepped with carries; ew_nd<VEC=1> for flat (1-D) streams.
+//   ew_run           anything else: 8 consecutive outputs per thread, every operand addressed in the cheapest
+//                    way its layout allows (modes 0..4); ew_nd<VEC=1> for flat (1-D) streams.
+//   ew_period        short inner axes under an operand outside ew_run's cheap modes ([N,1,7] + [1,9,7]): values
+//                    or offsets of one period of the innermost axes tabulated in shared memory, four shifted
+//                    copies so that 4 consecutive entries are always one aligned 128-bit load.
+//   ew_heavy_stream  contiguous streams under pow (optionally the FP64 ufuncs): persistent CTAs that keep the
+//                    next batch's loads in flight while they compute.
+// The libm functors (exp ... atanh, pow) answer from the certified short FP64 kernels of fast_ufunc.h / fast_pow.h.
 #pragma once
 #include <type_traits>
 
