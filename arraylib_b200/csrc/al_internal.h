@@ -43,6 +43,7 @@ struct Runtime {
     long disable_window = 0;
     long window_whole_blocks = 0;  // 1: fixed-w windows use the whole-block scan kernel instead of the half-block one
     long window_shfl = 1;      // fixed-w windows: 1..4 = register/shuffle kernel (cp.async ring shapes), 0 = shared-memory scan kernels
+    long window_any_l16 = 1;   // generic-w window kernel: 16 elements per lane for w < 24 (0: always 32)
     long window_ctas_per_sm = 0;  // 0 = default (32 CTAs per SM, 4 of them resident)
     long tile64 = 1;           // 0: use the 32x32 scalar transpose tile even when the float4 one applies
     long tile_tq = 64;         // q extent of the 128-bit transpose tile: 32, 64 or 128 (p extent = 4096 / tq)

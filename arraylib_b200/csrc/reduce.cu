@@ -717,16 +717,20 @@ reduce_window_half_kernel(const float* __restrict__ x, float* __restrict__ out, 
 // a block boundary, so the positions of the block boundaries inside a lane's chunk depend on (lane, w)
 // only and are kept as two 32-bit masks. The old kernel (one lane scans one whole block serially) ran a
 // 100-wide window at 1.8 TB/s because only nblk of its 256 lanes had work during the scans.
-constexpr int kAnyT = 128, kAnyL = 32, kAnySpan = kAnyT * kAnyL, kAnyPadded = kAnySpan + kAnySpan / 32;
+// L = 32 elements per lane needs 128 registers (4 CTAs of 128 threads per SM: ncu showed 24 % occupancy, the shared-memory
+// round trips exposed as `short_scoreboard` / `wait` stalls, issue slots 64 % busy). The kernel is also instantiated with
+// L = 16 (tile of 2048 elements): half the registers, twice the warps. Measured: +15 % at w = 12, nothing from w = 24 on
+// (4.1-4.3 TB/s either way: the shared-memory traffic, not the occupancy, is what binds), so only w < 24 uses it.
+constexpr int kAnyT = 128;
 
-template <int OP>
-__global__ void __launch_bounds__(kAnyT, 4)
+template <int OP, int L>
+__global__ void __launch_bounds__(kAnyT, L == 32 ? 4 : 7)
 reduce_window_any_kernel(const float* __restrict__ x, float* __restrict__ out, uint32_t nout, uint32_t w, uint32_t n_tiles,
                          uint32_t tiles_per_row, long long row_stride, float init, int init_is_identity) {
     extern __shared__ float wsm[];
-    constexpr int T = kAnyT, L = kAnyL, SPAN = kAnySpan, NW = kAnyT / 32;
+    constexpr int T = kAnyT, SPAN = kAnyT * L, NW = kAnyT / 32, PADDED = SPAN + SPAN / 32;
     float* P = wsm;               // staged elements, overwritten in place by the prefix scans
-    float* S = wsm + kAnyPadded;  // suffix scans
+    float* S = wsm + PADDED;      // suffix scans
     __shared__ float inc[2][T];   // inclusive cross-lane scan values: [0] left-to-right, [1] right-to-left
     __shared__ float wtot[2][NW];
     __shared__ int wflag[2][NW];
@@ -770,7 +774,7 @@ reduce_window_any_kernel(const float* __restrict__ x, float* __restrict__ out, u
         __syncthreads();
         if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);
         float xr[L];
-        float* const mine = P + tid * (L + 1);
+        float* const mine = P + tid * L + (tid * L) / 32;  // one pad float per 32 elements: a chunk never straddles a pad
 #pragma unroll
         for (int k = 0; k < L; k++) xr[k] = mine[k];
         // 1. aggregates: al = fold of the elements after the last block start (all of them if none),
@@ -817,7 +821,7 @@ reduce_window_any_kernel(const float* __restrict__ x, float* __restrict__ out, u
         //    lane from beyond the tile does not exist, and the S values that would need it are never read)
         float runp = tid > 0 ? inc[0][tid - 1] : id;
         float runs = tid < T - 1 ? inc[1][tid + 1] : id;
-        float* const sfx = S + tid * (L + 1);
+        float* const sfx = S + tid * L + (tid * L) / 32;
 #pragma unroll
         for (int k = 0; k < L; k++) {
             const float before = ((starts >> k) & 1u) ? id : runp;  // exclusive prefix of element k
@@ -1113,7 +1117,9 @@ template <int OP>
 static bool launch_window_any(const float* src, float* out, uint32_t nout, uint32_t w, uint32_t rows, long long row_stride, float init) {
     const float ident_tab[AL_REDOP_COUNT] = {0.0f, -INFINITY, INFINITY, 1.0f};
     const int init_is_identity = memcmp(&init, &ident_tab[OP], sizeof(float)) == 0;
-    const uint32_t tile = kAnySpan - w;
+    const bool small = w < 24 && rt().window_any_l16;  // L = 16 elements per lane (tile 2048), else 32 (tile 4096)
+    const uint32_t span = (uint32_t)kAnyT * (small ? 16u : 32u);
+    const uint32_t tile = span - w;
     const unsigned tiles_per_row = (unsigned)(((uint64_t)nout + tile - 1) / tile);
     const uint64_t all_tiles = (uint64_t)tiles_per_row * rows;
     if (all_tiles >= (1ull << 31)) return set_error("NotImplementedError: too many window tiles"), false;
@@ -1121,8 +1127,9 @@ static bool launch_window_any(const float* src, float* out, uint32_t nout, uint3
     const long per_sm = rt().window_ctas_per_sm > 0 ? rt().window_ctas_per_sm : 32;
     unsigned blocks = (unsigned)(kNumSMs * per_sm);
     if (blocks > n_tiles) blocks = n_tiles;
-    const size_t smem = 2ull * kAnyPadded * sizeof(float);
-    reduce_window_any_kernel<OP><<<blocks, kAnyT, smem, rt().stream>>>(src, out, nout, w, n_tiles, tiles_per_row, row_stride, init, init_is_identity);
+    const size_t smem = 2ull * (span + span / 32) * sizeof(float);
+    if (small) reduce_window_any_kernel<OP, 16><<<blocks, kAnyT, smem, rt().stream>>>(src, out, nout, w, n_tiles, tiles_per_row, row_stride, init, init_is_identity);
+    else reduce_window_any_kernel<OP, 32><<<blocks, kAnyT, smem, rt().stream>>>(src, out, nout, w, n_tiles, tiles_per_row, row_stride, init, init_is_identity);
     note_launch("reduce_window_any");
     return check_launch("reduce_window_any");
 }
@@ -1474,41 +1481,78 @@ struct ZeroFixArgs {
     uint64_t nout, count;
 };
 
+// Zero-sign repair. A warp looks at 256 outputs per trip (two 128-bit loads per lane, both in flight) and only for a ZERO
+// result walks that output's reduced elements, 32 at a time, up to the first zero. (The first version gave every output a
+// whole warp, i.e. one dependent 4-byte load per warp and trip: 26 ms behind a 0.5 ms window reduce_max with 2^28 outputs.)
+__device__ __forceinline__ void zero_sign_fix_one(const float* __restrict__ src, float* __restrict__ out, const ZeroFixArgs& a,
+                                                  uint64_t o, float init, int init_is_zero, unsigned lane) {
+    if (init_is_zero) {  // a zero init is the first zero of the fold
+        if (lane == 0) out[o] = init;
+        return;
+    }
+    int64_t base = 0;
+    uint64_t rem = o;
+    for (int d = a.nkept - 1; d >= 0; d--) {
+        base += (int64_t)(rem % a.kext[d]) * a.kstride[d];
+        rem /= a.kext[d];
+    }
+    for (uint64_t r0 = 0; r0 < a.count; r0 += 32) {
+        const uint64_t r = r0 + lane;
+        float x = 1.0f;
+        if (r < a.count) {
+            int64_t off = base;
+            uint64_t q = r;
+            for (int d = a.nred - 1; d >= 0; d--) {
+                off += (int64_t)(q % a.rext[d]) * a.rstride[d];
+                q /= a.rext[d];
+            }
+            x = src[off];
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, x == 0.0f);
+        if (hit) {
+            const float first = __shfl_sync(0xffffffffu, x, __ffs(hit) - 1);
+            if (lane == 0) out[o] = first;
+            return;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 reduce_zero_sign_kernel(const float* __restrict__ src, float* __restrict__ out, const ZeroFixArgs a, float init, int init_is_zero) {
     const unsigned lane = threadIdx.x & 31;
     const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
-    for (uint64_t o = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); o < a.nout; o += warps) {
-        const float v = out[o];
-        if (v != 0.0f) continue;  // (NaN compares unequal too)
-        if (init_is_zero) {       // a zero init is the first zero of the fold
-            if (lane == 0) out[o] = init;
-            continue;
-        }
-        int64_t base = 0;
-        uint64_t rem = o;
-        for (int d = a.nkept - 1; d >= 0; d--) {
-            base += (int64_t)(rem % a.kext[d]) * a.kstride[d];
-            rem /= a.kext[d];
-        }
-        for (uint64_t r0 = 0; r0 < a.count; r0 += 32) {
-            const uint64_t r = r0 + lane;
-            float x = 1.0f;
-            if (r < a.count) {
-                int64_t off = base;
-                uint64_t q = r;
-                for (int d = a.nred - 1; d >= 0; d--) {
-                    off += (int64_t)(q % a.rext[d]) * a.rstride[d];
-                    q /= a.rext[d];
-                }
-                x = src[off];
+    const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // whole groups of 256 outputs through 128-bit loads (the output block is 16-byte aligned: a fresh allocation)
+    const uint64_t groups = (reinterpret_cast<uintptr_t>(out) & 15) == 0 ? a.nout / 256 : 0;
+    for (uint64_t g = warp; g < groups; g += warps) {
+        const uint64_t o0 = g * 256;
+        float4 q[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) q[u] = *reinterpret_cast<const float4*>(out + o0 + (u * 32 + lane) * 4);
+        const bool mine = q[0].x == 0.0f || q[0].y == 0.0f || q[0].z == 0.0f || q[0].w == 0.0f ||
+                          q[1].x == 0.0f || q[1].y == 0.0f || q[1].z == 0.0f || q[1].w == 0.0f;  // (NaN compares unequal too)
+        unsigned owners = __ballot_sync(0xffffffffu, mine);
+        while (owners) {  // rare: some lane holds a zero result
+            const int l = __ffs(owners) - 1;
+            owners &= owners - 1;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const float c[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (__shfl_sync(0xffffffffu, c[k], l) == 0.0f) zero_sign_fix_one(src, out, a, o0 + (u * 32 + l) * 4 + k, init, init_is_zero, lane);
             }
-            const unsigned hit = __ballot_sync(0xffffffffu, x == 0.0f);
-            if (hit) {
-                const float first = __shfl_sync(0xffffffffu, x, __ffs(hit) - 1);
-                if (lane == 0) out[o] = first;
-                break;
-            }
+        }
+    }
+    // the rest (and unaligned outputs): 32 outputs per trip
+    for (uint64_t o0 = groups * 256 + warp * 32; o0 < a.nout; o0 += warps * 32) {
+        const uint64_t o = o0 + lane;
+        const float v = o < a.nout ? out[o] : 1.0f;
+        unsigned zeros = __ballot_sync(0xffffffffu, v == 0.0f);
+        while (zeros) {
+            const int l = __ffs(zeros) - 1;
+            zeros &= zeros - 1;
+            zero_sign_fix_one(src, out, a, o0 + l, init, init_is_zero, lane);
         }
     }
 }
@@ -1533,7 +1577,7 @@ static bool fix_zero_sign(const NDArray* src, float* out, const bool* red, float
             a.nout *= e;
         }
     }
-    const uint64_t blocks = (a.nout + 7) / 8;
+    const uint64_t blocks = (a.nout + 8 * 256 - 1) / (8 * 256);  // 8 warps per CTA, 256 outputs per warp and trip
     const unsigned grid = (unsigned)std::min<uint64_t>(blocks, (uint64_t)kNumSMs * 8);
     reduce_zero_sign_kernel<<<grid, 256, 0, rt().stream>>>(src->ptr, out, a, init, custom_init && init == 0.0f);
     rt().launches++;  // counted, but al_last_kernel() keeps naming the reduction kernel the plan chose

@@ -727,6 +727,7 @@ int al_set_tuning(const char* key, long value) {
     else if (k == "reduce_peel") g_rt.reduce_peel = value;
     else if (k == "outer_tile") g_rt.outer_tile = value;
     else if (k == "period_plan") g_rt.period_plan = value;
+    else if (k == "window_any_l16") g_rt.window_any_l16 = value;
     else if (k == "heavy_stream") g_rt.heavy_stream = value;
     else if (k == "heavy_ctas_per_sm") g_rt.heavy_ctas_per_sm = value > 0 ? value : 0;
     else {

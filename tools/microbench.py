@@ -250,6 +250,22 @@ def bench_pcie():
     print(f"{'D2H 4 GiB pageable (fresh np.empty)':40s} {dt*1e3:8.1f} ms  {4*n/dt/1e9:6.1f} GB/s", flush=True)
 
 
+def bench_window_any():
+    """Window widths outside 8/16/32/64/128: 32 elements per lane (round-2 kernel) against 16 (w <= 128)."""
+    n = 1 << 28
+    base = rnd((n,), 1)
+    for w in (12, 100):
+        for l16 in (0, 1):
+            tune(window_any_l16=l16)
+            timed(lambda: base.as_strided(shape=(n - w + 1, w), stride=(1, 1)).reduce_sum(dims=[1]), 8 * n, f"window-{w} reduce_sum 2^28 window_any_l16={l16}", reps=3, warm=1)
+    tune(window_any_l16=1)
+    timed(lambda: base.as_strided(shape=(n - 99, 100), stride=(1, 1)).reduce_max(dims=[1]), 8 * n, "window-100 reduce_max 2^28", reps=3, warm=1)
+    timed(lambda: base.as_strided(shape=(n - 63, 64), stride=(1, 1)).reduce_max(dims=[1]), 8 * n, "window-64 reduce_max 2^28", reps=3, warm=1)
+    X = base.reshape((16, 512, 512, 64))
+    timed(lambda: X.reduce_max(dims=(3,)), 4 * n + 4 * (n // 64), "reduce_max [16,512,512,64] dims=(3,)", reps=3, warm=1)
+    timed(lambda: X.reduce_min(dims=(1, 2)), 4 * n, "reduce_min [16,512,512,64] dims=(1,2)", reps=3, warm=1)
+
+
 def bench_stock():
     """The stock signatures on pageable numpy arrays: upload alone, download alone, both at once (second host thread)."""
     import threading
