@@ -1,5 +1,6 @@
 """CPU tests of host-side logic: callable -> device-ufunc resolution."""
 import math
+import os
 import operator
 
 import numpy as np
@@ -79,3 +80,15 @@ def test_traced_comparisons_and_mod_build_instructions():
     assert [BINOPS[i[1]] for i in trace.insns] == ["ne", "mul"]
     with pytest.raises(TypeError):
         hash(lazy.TExpr(trace, -1))
+
+
+def test_streaming_host_copy_matches_memcpy(tmp_path):
+    """csrc/hostcopy.cpp: the staging ring's copy with non-temporal stores (head / 128-byte body / tail split) must move
+    exactly the bytes memcpy moves, for any size and any source / destination alignment, and touch nothing else."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "hostcopy_harness"
+    subprocess.check_call(["g++", "-O2", "-mavx2", "-o", str(exe), os.path.join(root, "tests", "csrc", "hostcopy_harness.cpp"),
+                           os.path.join(root, "arraylib_b200", "csrc", "hostcopy.cpp")])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "hostcopy ok" in out.stdout, out.stdout[-500:]
