@@ -89,8 +89,10 @@ __device__ __forceinline__ float binop_raw(float l, float r) {
     else if constexpr (OP == AL_POW) return pow_like_reference(l, r);
     // gcc's inline fmax / fmin: a NaN on the left yields the right operand (whatever it is), a NaN on the right
     // yields the left one, and on a +-0 tie the LEFT operand is returned
-    else if constexpr (OP == AL_MAX) return (l >= r || (r != r && l == l)) ? l : r;
-    else if constexpr (OP == AL_MIN) return (l <= r || (r != r && l == l)) ? l : r;
+    // (FMNMX ignores a NaN operand like fmax / fmin do; only the tie -- +0 against -0 -- needs the left operand put back.
+    // Two NaNs give the canonical NaN here; binop_apply replaces it by the right operand, which is what the reference returns.)
+    else if constexpr (OP == AL_MAX) return l == r ? l : fmaxf(l, r);
+    else if constexpr (OP == AL_MIN) return l == r ? l : fminf(l, r);
     else if constexpr (OP == AL_EQ) return l == r ? 1.0f : 0.0f;
     else if constexpr (OP == AL_NE) return l != r ? 1.0f : 0.0f;
     else if constexpr (OP == AL_GT) return l > r ? 1.0f : 0.0f;
@@ -121,7 +123,7 @@ __device__ __forceinline__ float binop_apply(float l, float r) {
         }
         return r != r ? nan_quiet(r) : nan_default_neg();
     } else if constexpr (OP == AL_MAX || OP == AL_MIN) {
-        return nan_quiet(res);  // the operand has been through fmax's float -> double conversion, which quiets it
+        return nan_quiet(r);  // both operands are NaN: the right one, quieted by fmax's float -> double conversion
     } else {
         return nan_like_sse(res, l, r);
     }
